@@ -1,0 +1,156 @@
+/* sfb200.h -- C ABI of libsfb200.so, the sm_100a engine behind the SlotFormer
+ * hot paths.
+ *
+ * The reference (pairlab/SlotFormer) is pure Python/PyTorch and has no FFI of
+ * its own; this header is the thin extension boundary
+ * BASELINE.json's north_star prescribes.  Each entry point names the reference
+ * operator it replaces (paths relative to /root/reference/slotformer):
+ *
+ *   sfb_sa_forward        SlotAttention.forward        base_slots/models/savi.py:56-102
+ *                         SlotAttentionWMask.forward   base_slots/models/steve.py:19-73
+ *   sfb_rollout_forward   SlotRollouter.forward        video_prediction/models/slotformer.py:85-126
+ *                         SingleStepSlotRollouter.forward
+ *                                                      video_prediction/models/single_step_slotformer.py:49-90
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (see SFB_E_*); nothing throws or aborts;
+ *   - every data pointer is a DEVICE pointer borrowed for the duration of the (asynchronous)
+ *     call; the library allocates nothing persistent -- scratch is caller-provided workspace;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work on it, never
+ *     synchronise the host (except the *_host convenience entry points, which say so);
+ *   - weight pointers are the reference state_dict tensors themselves (fp32, contiguous,
+ *     PyTorch [out_features, in_features] layout), field names = state_dict keys.
+ */
+#ifndef SFB200_H_
+#define SFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_VERSION 100 /* 0.1.0 */
+
+#define SFB_OK 0
+#define SFB_E_BAD_SHAPE (-1)        /* unsupported / inconsistent dimensions            */
+#define SFB_E_BAD_ALIGN (-2)        /* pointer or stride not 16-byte aligned            */
+#define SFB_E_UNSUPPORTED_ARCH (-3) /* device is not sm_100                             */
+#define SFB_E_WORKSPACE (-4)        /* workspace too small                              */
+#define SFB_E_NULL (-5)             /* required pointer is NULL                         */
+#define SFB_E_CUDA_BASE (-100)      /* -100 - cudaError_t                               */
+
+#define SFB_DTYPE_F32 0
+#define SFB_DTYPE_BF16 1
+
+#define SFB_RO_SLIDE 0 /* SlotRollouter: fixed window, drop oldest frame each step       */
+#define SFB_RO_GROW 1  /* SingleStepSlotRollouter: window grows up to cond_len frames    */
+
+int sfb_version(void);
+const char* sfb_strerror(int code);
+/* number of kernel launches this process has made through the library (bench.py's gpu_launches) */
+long long sfb_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* Hot path 1: Slot Attention                                                 */
+/* ------------------------------------------------------------------------- */
+/* Parameter set of reference SlotAttention.__init__ (savi.py:19-54). */
+typedef struct sfb_sa_weights {
+    const float* norm_inputs_weight; /* [C]    */
+    const float* norm_inputs_bias;   /* [C]    */
+    const float* project_q_0_weight; /* [D]   LayerNorm */
+    const float* project_q_0_bias;   /* [D]    */
+    const float* project_q_1_weight; /* [D,D] no bias   */
+    const float* project_k_weight;   /* [D,C] no bias   */
+    const float* project_v_weight;   /* [D,C] no bias   */
+    const float* gru_weight_ih;      /* [3D,D] gates r,z,n */
+    const float* gru_weight_hh;      /* [3D,D] */
+    const float* gru_bias_ih;        /* [3D]   */
+    const float* gru_bias_hh;        /* [3D]   */
+    const float* mlp_0_weight;       /* [D]   LayerNorm */
+    const float* mlp_0_bias;         /* [D]    */
+    const float* mlp_1_weight;       /* [Dm,D] */
+    const float* mlp_1_bias;         /* [Dm]   */
+    const float* mlp_3_weight;       /* [D,Dm] */
+    const float* mlp_3_bias;         /* [D]    */
+} sfb_sa_weights;
+
+/* Bytes of device workspace sfb_sa_forward needs (holds the folded projections). */
+size_t sfb_sa_workspace_bytes(int C, int D);
+
+/* Slot Attention forward for B independent frames.
+ *   feats        [B, N, C]  fp32 (feat_dtype = SFB_DTYPE_F32); rows contiguous, frame b at
+ *                feats + b*feat_batch_stride elements (savi.py:406 passes encoder_out[:, idx])
+ *   slots_in     [B, K, D]  fp32 initial slots          slots_out [B, K, D] fp32
+ *   seg_mask     NULL, or [B, K, N] fp32: softmax-over-slots attention of the LAST iteration,
+ *                before +eps / renormalisation (steve.py:54-55)
+ *   workspace    >= sfb_sa_workspace_bytes(C, D), 16-byte aligned
+ *   cluster_size 0 = choose; otherwise CTAs per frame (8 or 16)
+ * Supported: (C, D, Dm) in {(128,128,256), (192,192,384)}, 1 <= K <= 8, n_iter >= 1, N >= 1
+ * with ceil(N / cluster_size) small enough to keep a frame resident on chip (N <= 4096).
+ */
+int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
+                   const float* slots_in, float* slots_out, float* seg_mask,
+                   const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
+                   int n_iter, float eps, int cluster_size, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Hot path 2: autoregressive slot-Transformer rollout                        */
+/* ------------------------------------------------------------------------- */
+/* One nn.TransformerEncoderLayer(norm_first=True) (slotformer.py:72-78). */
+typedef struct sfb_ro_layer {
+    const float* self_attn_in_proj_weight;  /* [3d, d] packed q,k,v */
+    const float* self_attn_in_proj_bias;    /* [3d]    */
+    const float* self_attn_out_proj_weight; /* [d, d]  */
+    const float* self_attn_out_proj_bias;   /* [d]     */
+    const float* linear1_weight;            /* [F, d]  */
+    const float* linear1_bias;              /* [F]     */
+    const float* linear2_weight;            /* [d, F]  */
+    const float* linear2_bias;              /* [d]     */
+    const float* norm1_weight;              /* [d]     */
+    const float* norm1_bias;                /* [d]     */
+    const float* norm2_weight;              /* [d]     */
+    const float* norm2_bias;                /* [d]     */
+} sfb_ro_layer;
+
+#define SFB_RO_MAX_LAYERS 16
+
+/* Parameter set of reference SlotRollouter.__init__ (slotformer.py:51-83). */
+typedef struct sfb_ro_weights {
+    const float* in_proj_weight;  /* [d, Ds] */
+    const float* in_proj_bias;    /* [d]     */
+    const float* out_proj_weight; /* [Ds, d] */
+    const float* out_proj_bias;   /* [Ds]    */
+    /* per-token positional table [pe_frames*K, d]: enc_t_pe repeated per slot (+ enc_slots_pe
+     * when configured), exactly the `enc_pe` tensor built at slotformer.py:103-110 */
+    const float* enc_pe;
+    int num_layers;
+    sfb_ro_layer layers[SFB_RO_MAX_LAYERS];
+} sfb_ro_weights;
+
+/* Bytes of device workspace for the fp16 operand copies of the weights. */
+size_t sfb_rollout_workspace_bytes(int Ds, int d, int F, int num_layers);
+
+/* Convert the fp32 weights into the fp16 operand copies held in `workspace`.  Call again
+ * whenever a weight tensor changed; sfb_rollout_forward only reads the workspace + biases. */
+int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Autoregressive rollout for B independent clips.
+ *   hist      [B, T_h, K, Ds] fp32 burn-in slots        pred_out [B, pred_len, K, Ds] fp32
+ *   mode      SFB_RO_SLIDE: window = T_h frames (pe_frames = T_h)
+ *             SFB_RO_GROW : T_h must be 1, window grows to cond_len frames (pe_frames = cond_len),
+ *                           positional rows are the LAST rows of the table
+ *   Supported: Ds in {128,192}, d in {128,256}, d/heads in {16,32}, F % 64 == 0,
+ *              window tokens <= 128.
+ */
+int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights* w, int B,
+                        int T_h, int K, int Ds, int d, int F, int heads, int pred_len, int mode,
+                        int cond_len, const void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H_ */

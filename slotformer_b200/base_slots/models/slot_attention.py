@@ -1,0 +1,102 @@
+"""Slot Attention operators backed by the sm_100a cluster kernel.
+
+Drop-in for reference ``SlotAttention`` (slotformer/base_slots/models/savi.py:16-110) and
+``SlotAttentionWMask`` (slotformer/base_slots/models/steve.py:13-73): same constructor
+arguments, same sub-module names (hence identical ``state_dict`` keys), same call signature.
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ...engine import SA_WEIGHT_KEYS, SlotAttentionEngine
+
+
+class SlotAttention(nn.Module):
+    """Iterative cross-attention from K slots onto N feature vectors."""
+
+    def __init__(self, in_features, num_iterations, num_slots, slot_size, mlp_hidden_size,
+                 eps=1e-6):
+        super().__init__()
+        self.in_features = in_features
+        self.num_iterations = num_iterations
+        self.num_slots = num_slots
+        self.slot_size = slot_size
+        self.mlp_hidden_size = mlp_hidden_size
+        self.eps = eps
+        self.attn_scale = self.slot_size ** -0.5
+
+        # parameter containers only -- the math runs in libsfb200.so
+        self.norm_inputs = nn.LayerNorm(in_features)
+        self.project_q = nn.Sequential(nn.LayerNorm(slot_size),
+                                       nn.Linear(slot_size, slot_size, bias=False))
+        self.project_k = nn.Linear(in_features, slot_size, bias=False)
+        self.project_v = nn.Linear(in_features, slot_size, bias=False)
+        self.gru = nn.GRUCell(slot_size, slot_size)
+        self.mlp = nn.Sequential(nn.LayerNorm(slot_size),
+                                 nn.Linear(slot_size, mlp_hidden_size), nn.ReLU(),
+                                 nn.Linear(mlp_hidden_size, slot_size))
+        self._engine = SlotAttentionEngine()
+        self.cluster_size = 0   # 0 = let the engine choose (8 for C=128, 16 for C=192)
+
+    # -- helpers ---------------------------------------------------------- #
+    def _weights(self):
+        named = dict(self.named_parameters())
+        return {k: named[k] for k in SA_WEIGHT_KEYS}
+
+    def _needs_autograd(self, *tensors):
+        if not torch.is_grad_enabled():
+            return False
+        return any(t.requires_grad for t in tensors) or \
+            any(p.requires_grad for p in self.parameters())
+
+    def _autograd_forward(self, inputs, slots, return_mask):
+        """Differentiable restatement (GPU eager), used only when gradients are required:
+        the backward pass re-derives everything from these ops.  Same math as the kernel
+        (savi.py:65-100); the inference path never comes here."""
+        x = self.norm_inputs(inputs)
+        k, v = self.project_k(x), self.project_v(x)
+        B, K, D = slots.shape
+        mask = None
+        for it in range(self.num_iterations):
+            prev = slots
+            q = self.project_q(slots)
+            attn = F.softmax(self.attn_scale * torch.einsum('bnc,bmc->bnm', k, q), dim=-1)
+            if return_mask and it == self.num_iterations - 1:
+                mask = attn.detach().clone().permute(0, 2, 1)
+            attn = attn + self.eps
+            attn = attn / attn.sum(dim=1, keepdim=True)
+            upd = torch.einsum('bnm,bnc->bmc', attn, v)
+            slots = self.gru(upd.reshape(B * K, D), prev.reshape(B * K, D)).view(B, K, D)
+            slots = slots + self.mlp(slots)
+        return (slots, mask) if return_mask else slots
+
+    def _run(self, inputs, slots, return_mask):
+        assert inputs.dim() == 3 and slots.dim() == 3
+        if self._needs_autograd(inputs, slots):
+            return self._autograd_forward(inputs, slots, return_mask)
+        return self._engine.forward(
+            inputs.detach().float(), slots.detach().float(),
+            {k: v.detach() for k, v in self._weights().items()},
+            self.num_iterations, self.eps, self.mlp_hidden_size, return_mask=return_mask,
+            cluster_size=self.cluster_size)
+
+    def forward(self, inputs, slots):
+        """inputs [B, N, C] flattened per-pixel features; slots [B, K, D] initial slots.
+        Returns the updated slots [B, K, D]."""
+        return self._run(inputs, slots, return_mask=False)
+
+    @property
+    def dtype(self):
+        return self.project_k.weight.dtype
+
+    @property
+    def device(self):
+        return self.project_k.weight.device
+
+
+class SlotAttentionWMask(SlotAttention):
+    """Slot Attention that also returns the last iteration's slot-softmax attention
+    [B, K, N] (taken before +eps / renormalisation) as a segmentation mask."""
+
+    def forward(self, inputs, slots):
+        return self._run(inputs, slots, return_mask=True)

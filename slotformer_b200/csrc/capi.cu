@@ -1,0 +1,223 @@
+// C ABI of libsfb200.so (declared in include/sfb200.h).  Plain pointers and sizes only;
+// validation + launch; no host synchronisation, no persistent allocations.
+#include "../../include/sfb200.h"
+#include "sa_kernel.h"
+#include "ro_kernel.h"
+
+#include <atomic>
+#include <cstring>
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? SFB_OK : (SFB_E_CUDA_BASE - (int)e); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DevInfo { int ok; int smem_optin; int sms; int cc; };
+
+// per-device properties, looked up once per device
+int device_info(DevInfo* out) {
+    static DevInfo cache[64];
+    static std::atomic<int> ready[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_err(e);
+    if (dev < 0 || dev >= 64) return SFB_E_UNSUPPORTED_ARCH;
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        DevInfo d{};
+        int major = 0, minor = 0;
+        if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return cuda_err(e);
+        if ((e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) return cuda_err(e);
+        if ((e = cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return cuda_err(e);
+        if ((e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return cuda_err(e);
+        d.cc = major * 10 + minor;
+        d.ok = 1;
+        cache[dev] = d;
+        ready[dev].store(1, std::memory_order_release);
+    }
+    *out = cache[dev];
+    return SFB_OK;
+}
+
+size_t sa_ws_qk_bytes(int C, int D) { return (size_t)C * D * sizeof(float); }
+
+}  // namespace
+
+extern "C" {
+
+int sfb_version(void) { return SFB_VERSION; }
+
+long long sfb_launch_count(void) { return g_launches.load(); }
+
+const char* sfb_strerror(int code) {
+    switch (code) {
+        case SFB_OK: return "ok";
+        case SFB_E_BAD_SHAPE: return "unsupported or inconsistent shape";
+        case SFB_E_BAD_ALIGN: return "pointer or stride is not 16-byte aligned";
+        case SFB_E_UNSUPPORTED_ARCH: return "device is not sm_100 (B200)";
+        case SFB_E_WORKSPACE: return "workspace too small";
+        case SFB_E_NULL: return "required pointer is NULL";
+        default: break;
+    }
+    if (code <= SFB_E_CUDA_BASE) return cudaGetErrorString((cudaError_t)(SFB_E_CUDA_BASE - code));
+    return "unknown error";
+}
+
+// ------------------------------------------------------------------------------------------
+// Slot Attention
+// ------------------------------------------------------------------------------------------
+size_t sfb_sa_workspace_bytes(int C, int D) {
+    if (C <= 0 || D <= 0) return 0;
+    return sa_ws_qk_bytes(C, D) + (size_t)3 * D * C * sizeof(float);
+}
+
+int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
+                   const float* slots_in, float* slots_out, float* seg_mask,
+                   const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
+                   int n_iter, float eps, int cluster_size, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    if (!feats || !slots_in || !slots_out || !w || !workspace) return SFB_E_NULL;
+    const float* const* wp = reinterpret_cast<const float* const*>(w);
+    for (size_t i = 0; i < sizeof(sfb_sa_weights) / sizeof(const float*); ++i)
+        if (!wp[i]) return SFB_E_NULL;
+    if (B < 0 || N < 1 || K < 1 || K > 8 || n_iter < 1) return SFB_E_BAD_SHAPE;
+    if (feat_dtype != SFB_DTYPE_F32) return SFB_E_BAD_SHAPE;
+    if (feat_batch_stride < (int64_t)N * C || (feat_batch_stride & 3)) return SFB_E_BAD_ALIGN;
+    if (!aligned16(feats) || !aligned16(slots_in) || !aligned16(slots_out) || !aligned16(workspace))
+        return SFB_E_BAD_ALIGN;
+    if (!aligned16(w->project_q_1_weight) || !aligned16(w->gru_weight_hh) || !aligned16(w->mlp_1_weight) ||
+        !aligned16(w->mlp_3_weight))
+        return SFB_E_BAD_ALIGN;
+    if (workspace_bytes < sfb_sa_workspace_bytes(C, D)) return SFB_E_WORKSPACE;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
+    if (B == 0) return SFB_OK;
+
+    sfb::SAPlan plan;
+    if (sfb::sa_plan(N, C, D, Dm, cluster_size, di.smem_optin, &plan)) return SFB_E_BAD_SHAPE;
+
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float* w_qk = reinterpret_cast<float*>(workspace);
+    float* w_iv = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sa_ws_qk_bytes(C, D));
+    cudaError_t e = sfb::sa_fold_launch(w->project_q_1_weight, w->project_k_weight, w->project_v_weight,
+                                        w->gru_weight_ih, w_qk, w_iv, C, D, st);
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
+
+    sfb::SAParams p{};
+    p.feats = reinterpret_cast<const float*>(feats);
+    p.feat_bstride = feat_batch_stride;
+    p.slots_in = slots_in;
+    p.slots_out = slots_out;
+    p.seg_mask = seg_mask;
+    p.ln_in_w = w->norm_inputs_weight; p.ln_in_b = w->norm_inputs_bias;
+    p.ln_q_w = w->project_q_0_weight;  p.ln_q_b = w->project_q_0_bias;
+    p.w_qk = w_qk; p.w_iv = w_iv;
+    p.w_hh = w->gru_weight_hh; p.b_ih = w->gru_bias_ih; p.b_hh = w->gru_bias_hh;
+    p.ln_m_w = w->mlp_0_weight; p.ln_m_b = w->mlp_0_bias;
+    p.w1 = w->mlp_1_weight; p.b1 = w->mlp_1_bias; p.w2 = w->mlp_3_weight; p.b2 = w->mlp_3_bias;
+    p.B = B; p.N = N; p.K = K; p.n_iter = n_iter; p.eps = eps;
+    p.rows_cta = plan.rows_cta; p.nstage = plan.nstage; p.lay = plan.lay;
+    e = sfb::sa_launch(p, plan, C, 0, st);
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
+    return SFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Rollout
+// ------------------------------------------------------------------------------------------
+static size_t ro_ws_elems(int Ds, int d, int F, int layers) {
+    return (size_t)d * Ds * 2 + (size_t)layers * ((size_t)3 * d * d + (size_t)d * d + (size_t)2 * F * d);
+}
+
+size_t sfb_rollout_workspace_bytes(int Ds, int d, int F, int num_layers) {
+    if (Ds <= 0 || d <= 0 || F <= 0 || num_layers <= 0) return 0;
+    return ro_ws_elems(Ds, d, F, num_layers) * sizeof(__half);
+}
+
+// workspace layout (fp16): w_in [d][Ds] | w_out [Ds][d] | per layer: wqkv [3d][d], wo [d][d], w1 [F][d], w2 [d][F]
+int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!w || !workspace) return SFB_E_NULL;
+    if (w->num_layers < 1 || w->num_layers > SFB_RO_MAX_LAYERS) return SFB_E_BAD_SHAPE;
+    if (workspace_bytes < sfb_rollout_workspace_bytes(Ds, d, F, w->num_layers)) return SFB_E_WORKSPACE;
+    if (!aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    if (!w->in_proj_weight || !w->out_proj_weight) return SFB_E_NULL;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    __half* dst = reinterpret_cast<__half*>(workspace);
+    struct Job { const float* src; size_t n; };
+    cudaError_t e;
+    auto run = [&](const float* src, size_t n) -> int {
+        if (!src) return SFB_E_NULL;
+        e = sfb::ro_convert_launch(src, dst, n, st);
+        if (e != cudaSuccess) return cuda_err(e);
+        g_launches.fetch_add(1);
+        dst += n;
+        return SFB_OK;
+    };
+    int rc;
+    if ((rc = run(w->in_proj_weight, (size_t)d * Ds))) return rc;
+    if ((rc = run(w->out_proj_weight, (size_t)Ds * d))) return rc;
+    for (int l = 0; l < w->num_layers; ++l) {
+        const sfb_ro_layer& ly = w->layers[l];
+        if ((rc = run(ly.self_attn_in_proj_weight, (size_t)3 * d * d))) return rc;
+        if ((rc = run(ly.self_attn_out_proj_weight, (size_t)d * d))) return rc;
+        if ((rc = run(ly.linear1_weight, (size_t)F * d))) return rc;
+        if ((rc = run(ly.linear2_weight, (size_t)d * F))) return rc;
+    }
+    return SFB_OK;
+}
+
+int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights* w, int B,
+                        int T_h, int K, int Ds, int d, int F, int heads, int pred_len, int mode,
+                        int cond_len, const void* workspace, size_t workspace_bytes, void* stream) {
+    if (!hist || !pred_out || !w || !workspace) return SFB_E_NULL;
+    if (B < 0 || T_h < 1 || K < 1 || K > 16 || pred_len < 0) return SFB_E_BAD_SHAPE;
+    if (w->num_layers < 1 || w->num_layers > SFB_RO_MAX_LAYERS) return SFB_E_BAD_SHAPE;
+    if (mode != SFB_RO_SLIDE && mode != SFB_RO_GROW) return SFB_E_BAD_SHAPE;
+    if (mode == SFB_RO_GROW && (T_h != 1 || cond_len < 1)) return SFB_E_BAD_SHAPE;
+    if (!aligned16(hist) || !aligned16(pred_out) || !aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    if (workspace_bytes < sfb_rollout_workspace_bytes(Ds, d, F, w->num_layers)) return SFB_E_WORKSPACE;
+    if (!w->in_proj_bias || !w->out_proj_bias || !w->enc_pe) return SFB_E_NULL;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
+    if (B == 0 || pred_len == 0) return SFB_OK;
+
+    sfb::ROParams p{};
+    p.hist = hist; p.pred = pred_out;
+    const __half* ws = reinterpret_cast<const __half*>(workspace);
+    p.w_in = ws; ws += (size_t)d * Ds;
+    p.w_out = ws; ws += (size_t)Ds * d;
+    p.b_in = w->in_proj_bias; p.b_out = w->out_proj_bias; p.pe = w->enc_pe;
+    for (int l = 0; l < w->num_layers; ++l) {
+        const sfb_ro_layer& s = w->layers[l];
+        sfb::ROLayer& t = p.layer[l];
+        t.wqkv = ws; ws += (size_t)3 * d * d;
+        t.wo = ws; ws += (size_t)d * d;
+        t.w1 = ws; ws += (size_t)F * d;
+        t.w2 = ws; ws += (size_t)d * F;
+        t.bqkv = s.self_attn_in_proj_bias; t.bo = s.self_attn_out_proj_bias;
+        t.b1 = s.linear1_bias; t.b2 = s.linear2_bias;
+        t.ln1w = s.norm1_weight; t.ln1b = s.norm1_bias; t.ln2w = s.norm2_weight; t.ln2b = s.norm2_bias;
+        if (!t.bqkv || !t.bo || !t.b1 || !t.b2 || !t.ln1w || !t.ln1b || !t.ln2w || !t.ln2b) return SFB_E_NULL;
+    }
+    p.B = B; p.hist_tokens = T_h * K; p.K = K; p.Ds = Ds; p.d = d; p.F = F; p.heads = heads;
+    p.layers = w->num_layers; p.pred_len = pred_len; p.mode = mode;
+    p.cond_tokens = (mode == SFB_RO_GROW) ? cond_len * K : T_h * K;
+    p.pe_tokens = p.cond_tokens;
+    p.lmax = p.cond_tokens;
+    size_t smem = 0;
+    if (sfb::ro_plan(&p, di.smem_optin, &smem)) return SFB_E_BAD_SHAPE;
+    cudaError_t e = sfb::ro_launch(p, smem, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
+    return SFB_OK;
+}
+
+}  // extern "C"

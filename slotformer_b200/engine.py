@@ -1,0 +1,241 @@
+"""ctypes binding of libsfb200.so (include/sfb200.h) for torch tensors.
+
+PyTorch is used for device memory and streams only; every hot-path computation is a call
+into the hand-written sm_100a kernels.  There is no CPU / eager fallback: if the library is
+missing or the tensors are not on a CUDA device the functions raise.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'lib', 'libsfb200.so')
+_lib = None
+
+SFB_DTYPE_F32 = 0
+SFB_RO_SLIDE = 0
+SFB_RO_GROW = 1
+RO_MAX_LAYERS = 16
+
+SA_WEIGHT_KEYS = (
+    'norm_inputs.weight', 'norm_inputs.bias', 'project_q.0.weight', 'project_q.0.bias',
+    'project_q.1.weight', 'project_k.weight', 'project_v.weight', 'gru.weight_ih',
+    'gru.weight_hh', 'gru.bias_ih', 'gru.bias_hh', 'mlp.0.weight', 'mlp.0.bias',
+    'mlp.1.weight', 'mlp.1.bias', 'mlp.3.weight', 'mlp.3.bias')
+
+RO_LAYER_KEYS = (
+    'self_attn.in_proj_weight', 'self_attn.in_proj_bias', 'self_attn.out_proj.weight',
+    'self_attn.out_proj.bias', 'linear1.weight', 'linear1.bias', 'linear2.weight',
+    'linear2.bias', 'norm1.weight', 'norm1.bias', 'norm2.weight', 'norm2.bias')
+
+
+class SfbError(RuntimeError):
+    pass
+
+
+class _SAWeights(ctypes.Structure):
+    _fields_ = [(k.replace('.', '_'), ctypes.c_void_p) for k in SA_WEIGHT_KEYS]
+
+
+class _ROLayer(ctypes.Structure):
+    _fields_ = [(k.replace('.', '_'), ctypes.c_void_p) for k in RO_LAYER_KEYS]
+
+
+class _ROWeights(ctypes.Structure):
+    _fields_ = [('in_proj_weight', ctypes.c_void_p), ('in_proj_bias', ctypes.c_void_p),
+                ('out_proj_weight', ctypes.c_void_p), ('out_proj_bias', ctypes.c_void_p),
+                ('enc_pe', ctypes.c_void_p), ('num_layers', ctypes.c_int),
+                ('layers', _ROLayer * RO_MAX_LAYERS)]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load libsfb200.so (once).  Raises SfbError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise SfbError(f'{_LIB_PATH} is missing: run `python -m slotformer_b200.build` '
+                       '(there is no fallback path)')
+    lib = ctypes.CDLL(_LIB_PATH)
+    c = ctypes
+    lib.sfb_version.restype = c.c_int
+    lib.sfb_strerror.restype = c.c_char_p
+    lib.sfb_strerror.argtypes = [c.c_int]
+    lib.sfb_launch_count.restype = c.c_longlong
+    lib.sfb_sa_workspace_bytes.restype = c.c_size_t
+    lib.sfb_sa_workspace_bytes.argtypes = [c.c_int, c.c_int]
+    lib.sfb_sa_forward.restype = c.c_int
+    lib.sfb_sa_forward.argtypes = [
+        c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.POINTER(_SAWeights), c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
+        c.c_float, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.sfb_rollout_workspace_bytes.restype = c.c_size_t
+    lib.sfb_rollout_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int]
+    lib.sfb_rollout_prepare.restype = c.c_int
+    lib.sfb_rollout_prepare.argtypes = [c.POINTER(_ROWeights), c.c_int, c.c_int, c.c_int,
+                                        c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.sfb_rollout_forward.restype = c.c_int
+    lib.sfb_rollout_forward.argtypes = [
+        c.c_void_p, c.c_void_p, c.POINTER(_ROWeights), c.c_int, c.c_int, c.c_int, c.c_int,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t,
+        c.c_void_p]
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
+    return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_workspace_bytes',
+            'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
+            'sfb_rollout_forward']
+
+
+def launch_count():
+    return int(load().sfb_launch_count())
+
+
+def _check(code):
+    if code != 0:
+        raise SfbError(f'libsfb200: {load().sfb_strerror(code).decode()} (code {code})')
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda_f32(name, t):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise SfbError(f'{name} must be a CUDA tensor (the engine has no CPU path)')
+    if t.dtype != torch.float32:
+        raise SfbError(f'{name} must be float32, got {t.dtype}')
+
+
+def _weights_key(tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+# --------------------------------------------------------------------------- #
+# Slot Attention
+# --------------------------------------------------------------------------- #
+class SlotAttentionEngine:
+    """Per-module launcher state (workspace) for sfb_sa_forward."""
+
+    def __init__(self):
+        self._ws = None
+
+    def forward(self, feats, slots, weights, num_iterations, eps, mlp_hidden_size,
+                return_mask=False, cluster_size=0):
+        """feats [B,N,C] f32 (rows contiguous; batch stride free), slots [B,K,D] f32.
+
+        ``weights``: dict state_dict-key -> CUDA f32 tensor (SA_WEIGHT_KEYS).
+        Returns slots [B,K,D] (and seg mask [B,K,N] if ``return_mask``).
+        """
+        lib = load()
+        _require_cuda_f32('inputs', feats)
+        _require_cuda_f32('slots', slots)
+        if feats.dim() != 3 or slots.dim() != 3 or feats.shape[0] != slots.shape[0]:
+            raise SfbError(f'bad shapes: inputs {tuple(feats.shape)}, slots {tuple(slots.shape)}')
+        B, N, C = feats.shape
+        K, D = slots.shape[1], slots.shape[2]
+        if feats.stride(2) != 1 or feats.stride(1) != C:
+            feats = feats.contiguous()
+        bstride = feats.stride(0) if B > 1 else N * C
+        slots = slots.contiguous()
+        dev = feats.device
+        ws_bytes = int(lib.sfb_sa_workspace_bytes(C, D))
+        if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        wt = []
+        cw = _SAWeights()
+        for k in SA_WEIGHT_KEYS:
+            t = weights[k]
+            _require_cuda_f32(k, t)
+            t = t if t.is_contiguous() else t.contiguous()
+            wt.append(t)
+            setattr(cw, k.replace('.', '_'), t.data_ptr())
+        out = torch.empty((B, K, D), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, K, N), dtype=torch.float32, device=dev) if return_mask else None
+        with torch.cuda.device(dev):
+            rc = lib.sfb_sa_forward(
+                feats.data_ptr(), SFB_DTYPE_F32, bstride, slots.data_ptr(), out.data_ptr(),
+                mask.data_ptr() if return_mask else None, ctypes.byref(cw), B, N, C, D,
+                int(mlp_hidden_size), K, int(num_iterations), float(eps), int(cluster_size),
+                self._ws.data_ptr(), ws_bytes, _stream(dev))
+        _check(rc)
+        if return_mask:
+            return out, mask
+        return out
+
+
+# --------------------------------------------------------------------------- #
+# Rollout
+# --------------------------------------------------------------------------- #
+class RolloutEngine:
+    """Per-module launcher state for sfb_rollout_prepare / sfb_rollout_forward."""
+
+    def __init__(self):
+        self._ws = None
+        self._key = None
+
+    def forward(self, hist, weights, enc_pe, num_layers, num_heads, pred_len, mode='slide',
+                cond_len=0):
+        """hist [B,T_h,K,Ds] f32 -> [B,pred_len,K,Ds] f32.
+
+        ``weights``: dict of SlotRollouter state_dict keys -> CUDA f32 tensors.
+        ``enc_pe``: per-token positional table [pe_frames*K, d] f32.
+        """
+        lib = load()
+        _require_cuda_f32('x', hist)
+        if hist.dim() != 4:
+            raise SfbError(f'x must be [B, T, K, Ds], got {tuple(hist.shape)}')
+        hist = hist.contiguous()
+        B, T_h, K, Ds = hist.shape
+        dev = hist.device
+        d = weights['in_proj.weight'].shape[0]
+        F = weights['transformer_encoder.layers.0.linear1.weight'].shape[0]
+        cw = _ROWeights()
+        keep = []
+
+        def ptr(name):
+            t = weights[name]
+            _require_cuda_f32(name, t)
+            t = t if t.is_contiguous() else t.contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        cw.in_proj_weight = ptr('in_proj.weight')
+        cw.in_proj_bias = ptr('in_proj.bias')
+        cw.out_proj_weight = ptr('out_proj.weight')
+        cw.out_proj_bias = ptr('out_proj.bias')
+        _require_cuda_f32('enc_pe', enc_pe)
+        enc_pe = enc_pe.contiguous()
+        cw.enc_pe = enc_pe.data_ptr()
+        cw.num_layers = int(num_layers)
+        if num_layers > RO_MAX_LAYERS:
+            raise SfbError(f'num_layers {num_layers} > {RO_MAX_LAYERS}')
+        for i in range(num_layers):
+            for k in RO_LAYER_KEYS:
+                setattr(cw.layers[i], k.replace('.', '_'),
+                        ptr(f'transformer_encoder.layers.{i}.{k}'))
+        ws_bytes = int(lib.sfb_rollout_workspace_bytes(Ds, d, F, num_layers))
+        out = torch.empty((B, pred_len, K, Ds), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
+                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                self._key = None
+            key = _weights_key(keep)
+            if key != self._key:
+                _check(lib.sfb_rollout_prepare(ctypes.byref(cw), Ds, d, F, self._ws.data_ptr(),
+                                               ws_bytes, _stream(dev)))
+                self._key = key
+            rc = lib.sfb_rollout_forward(
+                hist.data_ptr(), out.data_ptr(), ctypes.byref(cw), B, T_h, K, Ds, d, F,
+                int(num_heads), int(pred_len), SFB_RO_GROW if mode == 'grow' else SFB_RO_SLIDE,
+                int(cond_len or 0), self._ws.data_ptr(), ws_bytes, _stream(dev))
+        _check(rc)
+        return out

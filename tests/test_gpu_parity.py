@@ -1,0 +1,153 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the oracle and against the
+golden vectors produced by the unmodified reference.
+
+Tolerances (stated per BASELINE.json north_star, 'within 1e-3 rel'): metric is
+max|out-ref| / max|ref| (helpers.rel_max).
+  * Slot Attention slots           <= 1e-3  (fp16 tensor-core operands, fp32 everything else)
+  * Slot Attention seg mask        <= 2e-3  absolute (mask values are probabilities in [0,1])
+  * rollout, first predicted step  <= 1.5e-3
+  * rollout, free running <=64 steps <= 4e-3 (error compounds through the autoregression)
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from helpers import golden, rel_max, ro_module, sa_module
+from oracle import slot_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('name', list(cases.SA_CASES))
+def test_slot_attention_vs_reference_golden(name):
+    c, w, feats, slots = cases.sa_case(name)
+    g = golden(name)
+    m = sa_module(c, w, DEV)
+    with torch.no_grad():
+        out = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
+    if c['mask']:
+        out, mask = out
+        assert mask.shape == (c['B'], c['K'], c['N'])
+        assert np.abs(mask.cpu().numpy() - g['mask_f64']).max() < 2e-3
+    assert out.shape == (c['B'], c['K'], c['D'])
+    assert rel_max(out.cpu().numpy(), g['slots_f64']) < 1e-3
+
+
+@pytest.mark.parametrize('name', ['sa_tiny', 'sa_ragged'])
+def test_slot_attention_vs_oracle(name):
+    c, w, feats, slots = cases.sa_case(name)
+    ref = O.slot_attention(feats, slots, w, c['iters'])
+    m = sa_module(c, w, DEV, mask=False)
+    with torch.no_grad():
+        out = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
+    assert rel_max(out.cpu().numpy(), ref) < 1e-3
+
+
+def test_slot_attention_cluster16_and_strided_input():
+    c, w, feats, slots = cases.sa_case('sa_cfg2')
+    g = golden('sa_cfg2')
+    m = sa_module(c, w, DEV)
+    # frames strided in a [B, T, N, C] tensor, like encoder_out[:, idx] (savi.py:406)
+    big = torch.zeros((c['B'], 3, c['N'], c['C']), device=DEV)
+    big[:, 1] = torch.from_numpy(feats).to(DEV)
+    with torch.no_grad():
+        out_strided = m(big[:, 1], torch.from_numpy(slots).to(DEV))
+        m.cluster_size = 16
+        out16 = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
+    assert rel_max(out_strided.cpu().numpy(), g['slots_f64']) < 1e-3
+    assert rel_max(out16.cpu().numpy(), g['slots_f64']) < 1e-3
+
+
+def test_slot_attention_full_size_properties():
+    """BASELINE config-2 size (384 frames x 4096 x 128): determinism, batch independence,
+    pixel-permutation invariance (Slot Attention is a set function of the pixels)."""
+    c, w, _, _ = cases.sa_case('sa_cfg2')
+    m = sa_module(c, w, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    B = 384
+    feats = torch.randn((B, 4096, 128), device=DEV, generator=gen)
+    slots = torch.randn((B, 6, 128), device=DEV, generator=gen)
+    with torch.no_grad():
+        a = m(feats, slots)
+        b = m(feats, slots)
+        assert torch.equal(a, b)
+        assert torch.isfinite(a).all()
+        # a frame's result does not depend on its position in the batch / its neighbours
+        idx = torch.tensor([17, 3, 383, 100], device=DEV)
+        sub = m(feats[idx].contiguous(), slots[idx].contiguous())
+        assert torch.equal(sub, a[idx])
+        perm = torch.randperm(4096, device=DEV, generator=gen)
+        p = m(feats[:8][:, perm].contiguous(), slots[:8].contiguous())
+    assert rel_max(p.cpu().numpy(), a[:8].cpu().numpy()) < 2e-4
+
+
+@pytest.mark.parametrize('name', list(cases.RO_CASES))
+def test_rollout_vs_reference_golden(name):
+    c, w, hist = cases.ro_case(name)
+    g = golden(name)
+    m = ro_module(c, w, DEV, enc_t_pe=g['enc_t_pe'])
+    with torch.no_grad():
+        out = m(torch.from_numpy(hist).to(DEV), c['pred_len']).cpu().numpy()
+    ref = g['pred_f64']
+    assert out.shape == ref.shape
+    assert rel_max(out[:, 0], ref[:, 0]) < 1.5e-3
+    assert rel_max(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize('name', ['ro_tiny', 'ro_pack'])
+def test_rollout_vs_oracle_with_operand_rounding(name):
+    """Against the oracle emulating fp16 GEMM operands the kernel must agree much tighter."""
+    c, w, hist = cases.ro_case(name)
+    g = golden(name)
+    w2 = dict(w)
+    w2['enc_t_pe'] = g['enc_t_pe']
+
+    def f16(x):
+        return x.astype(np.float16).astype(x.dtype)
+
+    ref = O.rollout(hist, w2, c['pred_len'], c['heads'], c['layers'], mode=c['mode'],
+                    cond_len=c['cond_len'], operand_round=f16)
+    m = ro_module(c, w, DEV, enc_t_pe=g['enc_t_pe'])
+    with torch.no_grad():
+        out = m(torch.from_numpy(hist).to(DEV), c['pred_len']).cpu().numpy()
+    assert rel_max(out, ref) < 1.5e-3
+
+
+def test_rollout_full_size_properties():
+    """BASELINE config-2 size (B=64): determinism, clip independence, and the sliding-window
+    identity  rollout(x, n)[:, 1:] == rollout(cat(x[:, 1:], rollout(x, 1)), n-1)."""
+    c, w, _ = cases.ro_case('ro_cfg2')
+    g = golden('ro_cfg2')
+    m = ro_module(c, w, DEV, enc_t_pe=g['enc_t_pe'])
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn((64, 6, 6, 128), device=DEV, generator=gen)
+    with torch.no_grad():
+        a = m(x, 10)
+        assert torch.equal(a, m(x, 10))
+        assert torch.isfinite(a).all()
+        sub = m(x[[5, 63, 0]].contiguous(), 10)
+        assert torch.equal(sub, a[[5, 63, 0]])
+        x2 = torch.cat([x[:, 1:], a[:, :1]], dim=1)
+        b = m(x2, 9)
+    assert torch.equal(b, a[:, 1:])
+
+
+def test_engine_rejects_cpu_tensors_and_bad_shapes():
+    from slotformer_b200.engine import SfbError
+    c, w, feats, slots = cases.sa_case('sa_tiny')
+    m = sa_module(c, w, DEV)
+    with torch.no_grad():
+        with pytest.raises(SfbError):
+            m(torch.from_numpy(feats), torch.from_numpy(slots))          # CPU tensors: no fallback
+        with pytest.raises(SfbError):
+            m(torch.zeros((2, 256, 96), device=DEV), torch.zeros((2, 4, 128), device=DEV))
+
+
+def test_empty_batch():
+    c, w, feats, slots = cases.sa_case('sa_tiny')
+    m = sa_module(c, w, DEV)
+    with torch.no_grad():
+        out = m(torch.zeros((0, 256, 128), device=DEV), torch.zeros((0, 4, 128), device=DEV))
+    assert out.shape == (0, 4, 128)
