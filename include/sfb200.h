@@ -52,6 +52,13 @@ const char* sfb_strerror(int code);
 /* number of kernel launches this process has made through the library (bench.py's gpu_launches) */
 long long sfb_launch_count(void);
 
+/* Debug / profiling aids (not part of the operator surface).
+ * sfb_debug_set_profile: device buffer of `capacity` uint64 that the NEXT forward calls fill with
+ * %globaltimer stamps at phase boundaries (cluster 0 / CTA 0); pass NULL to switch it off.
+ * sfb_debug_sa_max_clusters: co-resident clusters of the Slot Attention kernel (needs a GPU). */
+void sfb_debug_set_profile(void* device_buf, int capacity);
+int sfb_debug_sa_max_clusters(int C, int cluster_size);
+
 /* ------------------------------------------------------------------------- */
 /* Hot path 1: Slot Attention                                                 */
 /* ------------------------------------------------------------------------- */

@@ -10,6 +10,8 @@
 namespace {
 
 std::atomic<long long> g_launches{0};
+unsigned long long* g_prof = nullptr;   // debug timeline buffer (device), see sfb_debug_set_profile
+int g_prof_cap = 0;
 
 inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? SFB_OK : (SFB_E_CUDA_BASE - (int)e); }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -48,6 +50,15 @@ extern "C" {
 
 int sfb_version(void) { return SFB_VERSION; }
 
+void sfb_debug_set_profile(void* device_buf, int capacity) {
+    g_prof = reinterpret_cast<unsigned long long*>(device_buf);
+    g_prof_cap = device_buf ? capacity : 0;
+}
+
+int sfb_debug_sa_max_clusters(int C, int cluster_size) {
+    return sfb::sa_max_clusters(C, cluster_size);
+}
+
 long long sfb_launch_count(void) { return g_launches.load(); }
 
 const char* sfb_strerror(int code) {
@@ -77,6 +88,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
                    int n_iter, float eps, int cluster_size, void* workspace,
                    size_t workspace_bytes, void* stream) {
+    if (B == 0) return SFB_OK;
     if (!feats || !slots_in || !slots_out || !w || !workspace) return SFB_E_NULL;
     const float* const* wp = reinterpret_cast<const float* const*>(w);
     for (size_t i = 0; i < sizeof(sfb_sa_weights) / sizeof(const float*); ++i)
@@ -121,6 +133,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     p.w1 = w->mlp_1_weight; p.b1 = w->mlp_1_bias; p.w2 = w->mlp_3_weight; p.b2 = w->mlp_3_bias;
     p.B = B; p.N = N; p.K = K; p.n_iter = n_iter; p.eps = eps;
     p.rows_cta = plan.rows_cta; p.nstage = plan.nstage; p.lay = plan.lay;
+    p.prof = g_prof; p.prof_cap = g_prof_cap;
     e = sfb::sa_launch(p, plan, C, 0, st);
     if (e != cudaSuccess) return cuda_err(e);
     g_launches.fetch_add(1);
@@ -175,6 +188,7 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
 int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights* w, int B,
                         int T_h, int K, int Ds, int d, int F, int heads, int pred_len, int mode,
                         int cond_len, const void* workspace, size_t workspace_bytes, void* stream) {
+    if (B == 0 || pred_len == 0) return SFB_OK;
     if (!hist || !pred_out || !w || !workspace) return SFB_E_NULL;
     if (B < 0 || T_h < 1 || K < 1 || K > 16 || pred_len < 0) return SFB_E_BAD_SHAPE;
     if (w->num_layers < 1 || w->num_layers > SFB_RO_MAX_LAYERS) return SFB_E_BAD_SHAPE;
@@ -212,6 +226,7 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     p.cond_tokens = (mode == SFB_RO_GROW) ? cond_len * K : T_h * K;
     p.pe_tokens = p.cond_tokens;
     p.lmax = p.cond_tokens;
+    p.prof = g_prof; p.prof_cap = g_prof_cap;
     size_t smem = 0;
     if (sfb::ro_plan(&p, di.smem_optin, &smem)) return SFB_E_BAD_SHAPE;
     cudaError_t e = sfb::ro_launch(p, smem, reinterpret_cast<cudaStream_t>(stream));

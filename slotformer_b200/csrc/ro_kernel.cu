@@ -256,6 +256,9 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
     const int HG = p.hg, FC = p.fc;
     const int hgw = HG * DH;                  // columns per q/k/v group block
     const float sm_scale_log2 = rsqrtf((float)DH) * 1.4426950408889634f;
+    int pidx = 0;
+    const bool do_prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+#define RO_STAMP() do { if (do_prof && pidx < p.prof_cap) p.prof[pidx++] = globaltimer_ns(); } while (0)
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         const float* hist = p.hist + (size_t)b * p.hist_tokens * Ds;
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
             else { L = total < p.cond_tokens ? total : p.cond_tokens; base = total - L; pe0 = p.pe_tokens - L; }
             const int Lp = (L + 15) & ~15, nmb = Lp >> 4, nkb = Lp >> 3;
 
+            RO_STAMP();   // step start
             // ---- window tokens -> fp16 A tile (rows >= L zeroed) ----
             for (int i = tid; i < Lp * (Ds / 4); i += RO_THREADS) {
                 const int r = i / (Ds / 4), c4 = (i % (Ds / 4)) * 4;
@@ -297,11 +301,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
                          }, warp, lane);
             __syncthreads();
 
+            RO_STAMP();   // in_proj done
             for (int layer = 0; layer < p.layers; ++layer) {
                 const ROLayer& ly = p.layer[layer];
                 // ---- y = LN1(h) ----
                 ln_to_half<DMODEL>(h, abuf, lda, L, Lp, ly.ln1w, ly.ln1b, warp, lane);
                 __syncthreads();
+                RO_STAMP();   // LN1 done
                 // ---- self-attention, HG heads at a time ----
                 for (int h0 = 0; h0 < p.heads; h0 += HG) {
                     // q | k | v columns of this head group -> bbuf[:, 0:3*hgw]
@@ -315,12 +321,14 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
                                      }, warp, lane);
                     }
                     __syncthreads();
+                    RO_STAMP();   // qkv done
                     for (int item = warp; item < HG * nmb; item += RO_WARPS) {
                         const int hh = item / nmb, mb = item % nmb;
                         attn_block<DH, NKB>(bbuf, ldb, mb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb,
                                             sm_scale_log2, lane);
                     }
                     __syncthreads();
+                    RO_STAMP();   // attention done
                     // h += O_group Wo[:, group]^T (+ bias once)
                     const bool first = (h0 == 0);
                     cta_gemm_any(bbuf, ldb, nmb, ly.wo + h0 * DH, DMODEL, DMODEL, hgw,
@@ -336,9 +344,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
                                  }, warp, lane);
                     __syncthreads();
                 }
+                RO_STAMP();   // out-proj done
                 // ---- y = LN2(h);  h += W2 relu(W1 y + b1) + b2, FC hidden columns at a time ----
                 ln_to_half<DMODEL>(h, abuf, lda, L, Lp, ly.ln2w, ly.ln2b, warp, lane);
                 __syncthreads();
+                RO_STAMP();   // LN2 done
                 for (int f0 = 0; f0 < F; f0 += FC) {
                     const int fcw = (F - f0) < FC ? (F - f0) : FC;
                     cta_gemm_any(abuf, lda, nmb, ly.w1 + (size_t)f0 * DMODEL, DMODEL, fcw, DMODEL,
@@ -348,6 +358,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
                                          __floats2half2_rn(fmaxf(v0 + bi.x, 0.f), fmaxf(v1 + bi.y, 0.f));
                                  }, warp, lane);
                     __syncthreads();
+                    RO_STAMP();   // ffn1 chunk done
                     const bool first = (f0 == 0);
                     cta_gemm_any(bbuf, ldb, nmb, ly.w2 + f0, F, DMODEL, fcw,
                                  [&](int row, int col, float v0, float v1) {
@@ -364,6 +375,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) ro_forward_kernel(const ROParam
                 }
             }
 
+            RO_STAMP();   // layers done
             // ---- out_proj on the last K tokens -> pred_out[b, step] (slotformer.py:121) ----
             for (int i = tid; i < 16 * DMODEL; i += RO_THREADS) {
                 const int r = i / DMODEL, c = i % DMODEL;

@@ -28,6 +28,8 @@ struct ROParams {
     int lmax;            // max window tokens over the rollout
     int lda, ldb;        // row strides (halves) of the fp16 activation buffers
     uint32_t off_h, off_a, off_b;   // shared-memory byte offsets
+    unsigned long long* prof;       // optional timeline buffer (debug), CTA 0 / thread 0
+    int prof_cap;
     ROLayer layer[RO_MAX_LAYERS];
 };
 

@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
     const uint32_t slab_u32 = smem_u32(slab);
     uint32_t nsync = 0;
     uint32_t ntile_g = 0;
+    int pidx = 0;
+    const bool do_prof = (p.prof != nullptr) && cid == 0 && crank == 0 && tid == 0;
+#define SA_STAMP() do { if (do_prof && pidx < p.prof_cap) p.prof[pidx++] = globaltimer_ns(); } while (0)
 
     for (int f = cid; f < p.B; f += ncl) {
         // ---- initial slots -> s_cur (every CTA keeps the full K x D state) ----
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
             s_cur[i] = __ldg(p.slots_in + (size_t)f * K * D + i);
         consumer_bar();
 
+        SA_STAMP();   // 0: frame start (slots loaded)
         float xs_own = 0.f;   // reduced sum_n x^[n][c] for the channel this thread owns (tid < 8*Cc)
 
         for (int it = 0; it < p.n_iter; ++it) {
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
                            });
                 cluster_sync_consumers(cbar, nsync, CS, tid);
             }
+            SA_STAMP();   // 1: q~ all-gathered
 
             // ================= attention pass over this CTA's pixels =================
             uint32_t bq_hi[KS][2], bq_lo[KS][2];
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
                 }
             }
 
+            SA_STAMP();   // 2: pass done
             // ================= CTA-level reduction of the pass partials =================
             // column sums: reduce over g (lanes sharing t4), then one row per warp
             cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
@@ -465,6 +471,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
                 consumer_bar();
                 if (warp == 0) add(1);
             }
+            SA_STAMP();   // 3: CTA tree reduction done
             // ================= E1: reduce-scatter U^T (by channel owner) + colsum / xsum =========
             if (warp == 0) {
                 const uint32_t rs_u32 = smem_u32(rs_buf);
@@ -495,6 +502,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
             }
             cluster_sync_consumers(cbar, nsync, CS, tid);
 
+            SA_STAMP();   // 4: E1 synced
             // ================= owner reduce -> u^ slice, E2: all-gather u^ =================
             if (tid < 8 * Cc) {
                 const int slot = tid / Cc, cl = tid % Cc;
@@ -518,6 +526,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
             }
             cluster_sync_consumers(cbar, nsync, CS, tid);
 
+            SA_STAMP();   // 5: E2 synced (u^ everywhere)
             // ================= step A: GRU gates for this CTA's Dc columns =================
             rowdots<C>(p.w_iv, 3 * Dc, uhat, tid,
                        [&](int r) { return (r / Dc) * D + (int)crank * Dc + (r % Dc); },
@@ -539,6 +548,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
             }
             cluster_sync_consumers(cbar, nsync, CS, tid);
 
+            SA_STAMP();   // 6: step A + E3
             // ================= step B: hidden slice of the residual MLP =================
             ln_rows<D>(sprime, lnbuf, p.ln_m_w, p.ln_m_b, K, warp, lane);
             consumer_bar();
@@ -554,6 +564,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
                        });
             cluster_sync_consumers(cbar, nsync, CS, tid);
 
+            SA_STAMP();   // 7: step B + E4
             // ================= step C: new slots slice =================
             const bool last = (it == p.n_iter - 1);
             rowdots<DM>(p.w2, Dc, h1, tid,
@@ -570,6 +581,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_forward_kernel(const SAParam
                                 }
                             }
                         });
+            SA_STAMP();   // 8: step C done (before E5 sync)
             if (last) {
                 // peers may still read sprime / h1 of this iteration; the next frame's first
                 // remote writes (q~) go to qfrag only, and its first cluster sync orders the rest.
@@ -627,7 +639,7 @@ int sa_plan(int N, int C, int D, int DM, int cluster_size, int smem_limit, SAPla
 }
 
 template <int C, int D, int DM>
-static cudaError_t launch_t(const SAParams& p, const SAPlan& plan, int max_clusters_hint, cudaStream_t st) {
+static cudaError_t config_t(const SAPlan& plan, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int* max_clusters) {
     auto kern = sa_forward_kernel<C, D, DM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -635,38 +647,62 @@ static cudaError_t launch_t(const SAParams& p, const SAPlan& plan, int max_clust
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(SA_THREADS);
-    cfg.dynamicSmemBytes = plan.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    *cfg = cudaLaunchConfig_t{};
+    cfg->blockDim = dim3(SA_THREADS);
+    cfg->dynamicSmemBytes = plan.smem_bytes;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = plan.cluster_size;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
     // persistent: as many clusters as can be co-resident (cached per configuration)
     static int cached_clusters[2][2] = {{0, 0}, {0, 0}};
     int& nc = cached_clusters[C == 128 ? 0 : 1][plan.cluster_size == 8 ? 0 : 1];
     if (nc == 0) {
-        cfg.gridDim = dim3(plan.cluster_size * 8);
+        cfg->gridDim = dim3(plan.cluster_size * 8);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, kern, cfg);
         if (e != cudaSuccess) return e;
         if (n < 1) return cudaErrorLaunchOutOfResources;
         nc = n;
     }
-    int ncl = nc;
+    *max_clusters = nc;
+    return cudaSuccess;
+}
+
+template <int C, int D, int DM>
+static cudaError_t launch_t(const SAParams& p, const SAPlan& plan, int max_clusters_hint, cudaStream_t st) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int ncl = 0;
+    cudaError_t e = config_t<C, D, DM>(plan, &cfg, attr, &ncl);
+    if (e != cudaSuccess) return e;
+    cfg.stream = st;
     if (max_clusters_hint > 0 && ncl > max_clusters_hint) ncl = max_clusters_hint;
     if (ncl > p.B) ncl = p.B;
     cfg.gridDim = dim3(ncl * plan.cluster_size);
-    return cudaLaunchKernelEx(&cfg, kern, p);
+    return cudaLaunchKernelEx(&cfg, sa_forward_kernel<C, D, DM>, p);
 }
 
 cudaError_t sa_launch(const SAParams& p, const SAPlan& plan, int C, int max_clusters_hint, cudaStream_t st) {
     if (C == 128) return launch_t<128, 128, 256>(p, plan, max_clusters_hint, st);
     return launch_t<192, 192, 384>(p, plan, max_clusters_hint, st);
+}
+
+int sa_max_clusters(int C, int cluster_size) {
+    int dev = 0, smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    SAPlan plan;
+    const int D = C, DM = 2 * C;
+    if (sa_plan(4096, C, D, DM, cluster_size, smem, &plan)) return -1;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int ncl = 0;
+    cudaError_t e = (C == 128) ? config_t<128, 128, 256>(plan, &cfg, attr, &ncl)
+                               : config_t<192, 192, 384>(plan, &cfg, attr, &ncl);
+    return e == cudaSuccess ? ncl : -1;
 }
 
 cudaError_t sa_fold_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,

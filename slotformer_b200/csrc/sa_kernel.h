@@ -35,10 +35,13 @@ struct SAParams {
     float eps;
     int rows_cta, nstage;
     SALayout lay;
+    unsigned long long* prof;   // optional timeline buffer (debug), cluster 0 / CTA 0 / thread 0
+    int prof_cap;
 };
 
 int sa_plan(int N, int C, int D, int DM, int cluster_size, int smem_limit, SAPlan* plan);
 cudaError_t sa_launch(const SAParams& p, const SAPlan& plan, int C, int max_clusters_hint, cudaStream_t st);
+int sa_max_clusters(int C, int cluster_size);
 cudaError_t sa_fold_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,
                            float* w_qk, float* w_iv, int C, int D, cudaStream_t st);
 

@@ -67,6 +67,10 @@ def load():
     lib.sfb_strerror.restype = c.c_char_p
     lib.sfb_strerror.argtypes = [c.c_int]
     lib.sfb_launch_count.restype = c.c_longlong
+    lib.sfb_debug_set_profile.restype = None
+    lib.sfb_debug_set_profile.argtypes = [c.c_void_p, c.c_int]
+    lib.sfb_debug_sa_max_clusters.restype = c.c_int
+    lib.sfb_debug_sa_max_clusters.argtypes = [c.c_int, c.c_int]
     lib.sfb_sa_workspace_bytes.restype = c.c_size_t
     lib.sfb_sa_workspace_bytes.argtypes = [c.c_int, c.c_int]
     lib.sfb_sa_forward.restype = c.c_int
@@ -90,7 +94,8 @@ def load():
 
 def exported_symbols():
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
-    return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_workspace_bytes',
+    return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_debug_set_profile',
+            'sfb_debug_sa_max_clusters', 'sfb_sa_workspace_bytes',
             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
             'sfb_rollout_forward']
 
@@ -147,6 +152,9 @@ class SlotAttentionEngine:
         bstride = feats.stride(0) if B > 1 else N * C
         slots = slots.contiguous()
         dev = feats.device
+        if B == 0:
+            out = feats.new_zeros((0, K, D))
+            return (out, feats.new_zeros((0, K, N))) if return_mask else out
         ws_bytes = int(lib.sfb_sa_workspace_bytes(C, D))
         if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -196,6 +204,8 @@ class RolloutEngine:
         hist = hist.contiguous()
         B, T_h, K, Ds = hist.shape
         dev = hist.device
+        if B == 0 or pred_len == 0:
+            return hist.new_zeros((B, pred_len, K, Ds))
         d = weights['in_proj.weight'].shape[0]
         F = weights['transformer_encoder.layers.0.linear1.weight'].shape[0]
         cw = _ROWeights()
