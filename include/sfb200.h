@@ -55,9 +55,8 @@ long long sfb_launch_count(void);
 /* Debug / profiling aids (not part of the operator surface).
  * sfb_debug_set_profile: device buffer of `capacity` uint64 that the NEXT forward calls fill with
  * %globaltimer stamps at phase boundaries (cluster 0 / CTA 0); pass NULL to switch it off.
- * sfb_debug_sa_max_clusters: co-resident clusters of the Slot Attention kernel (needs a GPU). */
+ */
 void sfb_debug_set_profile(void* device_buf, int capacity);
-int sfb_debug_sa_max_clusters(int C, int cluster_size);
 
 /* ------------------------------------------------------------------------- */
 /* Hot path 1: Slot Attention                                                 */
@@ -83,8 +82,9 @@ typedef struct sfb_sa_weights {
     const float* mlp_3_bias;         /* [D]    */
 } sfb_sa_weights;
 
-/* Bytes of device workspace sfb_sa_forward needs (holds the folded projections). */
-size_t sfb_sa_workspace_bytes(int C, int D);
+/* Bytes of device workspace sfb_sa_forward needs: folded fp16 hi/lo weights, per-frame q~,
+ * per-(frame, pixel-chunk) partial sums and the fp16 x^ ring of one frame chunk. */
+size_t sfb_sa_workspace_bytes(int B, int N, int C, int D, int Dm, int n_iter, int chunk_frames);
 
 /* Slot Attention forward for B independent frames.
  *   feats        [B, N, C]  fp32 (feat_dtype = SFB_DTYPE_F32); rows contiguous, frame b at
@@ -92,15 +92,15 @@ size_t sfb_sa_workspace_bytes(int C, int D);
  *   slots_in     [B, K, D]  fp32 initial slots          slots_out [B, K, D] fp32
  *   seg_mask     NULL, or [B, K, N] fp32: softmax-over-slots attention of the LAST iteration,
  *                before +eps / renormalisation (steve.py:54-55)
- *   workspace    >= sfb_sa_workspace_bytes(C, D), 16-byte aligned
- *   cluster_size 0 = choose; otherwise CTAs per frame (8 or 16)
- * Supported: (C, D, Dm) in {(128,128,256), (192,192,384)}, 1 <= K <= 8, n_iter >= 1, N >= 1
- * with ceil(N / cluster_size) small enough to keep a frame resident on chip (N <= 4096).
+ *   workspace    >= sfb_sa_workspace_bytes(...) for the same arguments, 16-byte aligned
+ *   chunk_frames 0 = choose; otherwise frames processed per scheduling chunk (the fp16 x^ ring
+ *                of one chunk is what later iterations re-read; keep it inside L2)
+ * Supported: (C, D, Dm) in {(128,128,256), (192,192,384)}, 1 <= K <= 8, n_iter >= 1, N >= 1.
  */
 int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const float* slots_in, float* slots_out, float* seg_mask,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
-                   int n_iter, float eps, int cluster_size, void* workspace,
+                   int n_iter, float eps, int chunk_frames, void* workspace,
                    size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */

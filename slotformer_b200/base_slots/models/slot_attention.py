@@ -1,4 +1,4 @@
-"""Slot Attention operators backed by the sm_100a cluster kernel.
+"""Slot Attention operators backed by the sm_100a streaming kernels.
 
 Drop-in for reference ``SlotAttention`` (slotformer/base_slots/models/savi.py:16-110) and
 ``SlotAttentionWMask`` (slotformer/base_slots/models/steve.py:13-73): same constructor
@@ -36,7 +36,7 @@ class SlotAttention(nn.Module):
                                  nn.Linear(slot_size, mlp_hidden_size), nn.ReLU(),
                                  nn.Linear(mlp_hidden_size, slot_size))
         self._engine = SlotAttentionEngine()
-        self.cluster_size = 0   # 0 = let the engine choose (8 for C=128, 16 for C=192)
+        self.chunk_frames = 0   # 0 = let the engine size the frame chunks (fp16 x^ ring inside L2)
 
     # -- helpers ---------------------------------------------------------- #
     def _weights(self):
@@ -78,7 +78,7 @@ class SlotAttention(nn.Module):
             inputs.detach().float(), slots.detach().float(),
             {k: v.detach() for k, v in self._weights().items()},
             self.num_iterations, self.eps, self.mlp_hidden_size, return_mask=return_mask,
-            cluster_size=self.cluster_size)
+            chunk_frames=self.chunk_frames)
 
     def forward(self, inputs, slots):
         """inputs [B, N, C] flattened per-pixel features; slots [B, K, D] initial slots.

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -42,7 +43,6 @@ int device_info(DevInfo* out) {
     return SFB_OK;
 }
 
-size_t sa_ws_qk_bytes(int C, int D) { return (size_t)C * D * sizeof(float); }
 
 }  // namespace
 
@@ -55,9 +55,7 @@ void sfb_debug_set_profile(void* device_buf, int capacity) {
     g_prof_cap = device_buf ? capacity : 0;
 }
 
-int sfb_debug_sa_max_clusters(int C, int cluster_size) {
-    return sfb::sa_max_clusters(C, cluster_size);
-}
+
 
 long long sfb_launch_count(void) { return g_launches.load(); }
 
@@ -78,15 +76,27 @@ const char* sfb_strerror(int code) {
 // ------------------------------------------------------------------------------------------
 // Slot Attention
 // ------------------------------------------------------------------------------------------
-size_t sfb_sa_workspace_bytes(int C, int D) {
-    if (C <= 0 || D <= 0) return 0;
-    return sa_ws_qk_bytes(C, D) + (size_t)3 * D * C * sizeof(float);
+static int sa_pick_chunk(int B, int N, int C, int n_iter, int chunk_frames) {
+    (void)N; (void)C; (void)n_iter;
+    // Default: the whole batch is one scheduling chunk (passes and updates are full-GPU launches).
+    // Smaller chunks keep the fp16 x^ ring L2 resident but serialise the update kernels; they pay
+    // off only once chunks are overlapped on several streams ("next").
+    if (chunk_frames > 0) return chunk_frames < B ? chunk_frames : B;
+    return B;
+}
+
+size_t sfb_sa_workspace_bytes(int B, int N, int C, int D, int Dm, int n_iter, int chunk_frames) {
+    if (B <= 0 || N <= 0 || C <= 0 || D <= 0 || Dm <= 0 || n_iter <= 0) return 0;
+    sfb::SAWorkspace ws;
+    const int chunk = sa_pick_chunk(B, N, C, n_iter, chunk_frames);
+    sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);
+    return ws.total;
 }
 
 int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const float* slots_in, float* slots_out, float* seg_mask,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
-                   int n_iter, float eps, int cluster_size, void* workspace,
+                   int n_iter, float eps, int chunk_frames, void* workspace,
                    size_t workspace_bytes, void* stream) {
     if (B == 0) return SFB_OK;
     if (!feats || !slots_in || !slots_out || !w || !workspace) return SFB_E_NULL;
@@ -95,48 +105,71 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
         if (!wp[i]) return SFB_E_NULL;
     if (B < 0 || N < 1 || K < 1 || K > 8 || n_iter < 1) return SFB_E_BAD_SHAPE;
     if (feat_dtype != SFB_DTYPE_F32) return SFB_E_BAD_SHAPE;
+    if (!sfb::sa_shape_supported(C, D, Dm)) return SFB_E_BAD_SHAPE;
     if (feat_batch_stride < (int64_t)N * C || (feat_batch_stride & 3)) return SFB_E_BAD_ALIGN;
     if (!aligned16(feats) || !aligned16(slots_in) || !aligned16(slots_out) || !aligned16(workspace))
         return SFB_E_BAD_ALIGN;
-    if (!aligned16(w->project_q_1_weight) || !aligned16(w->gru_weight_hh) || !aligned16(w->mlp_1_weight) ||
-        !aligned16(w->mlp_3_weight))
-        return SFB_E_BAD_ALIGN;
-    if (workspace_bytes < sfb_sa_workspace_bytes(C, D)) return SFB_E_WORKSPACE;
+    if (workspace_bytes < sfb_sa_workspace_bytes(B, N, C, D, Dm, n_iter, chunk_frames)) return SFB_E_WORKSPACE;
     DevInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
     if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
-    if (B == 0) return SFB_OK;
 
-    sfb::SAPlan plan;
-    if (sfb::sa_plan(N, C, D, Dm, cluster_size, di.smem_optin, &plan)) return SFB_E_BAD_SHAPE;
-
+    const int chunk = sa_pick_chunk(B, N, C, n_iter, chunk_frames);
+    sfb::SAWorkspace ws;
+    sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);
+    char* base = reinterpret_cast<char*>(workspace);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    float* w_qk = reinterpret_cast<float*>(workspace);
-    float* w_iv = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sa_ws_qk_bytes(C, D));
-    cudaError_t e = sfb::sa_fold_launch(w->project_q_1_weight, w->project_k_weight, w->project_v_weight,
-                                        w->gru_weight_ih, w_qk, w_iv, C, D, st);
+
+    cudaError_t e = sfb::sa_prep_launch(w->project_q_1_weight, w->project_k_weight, w->project_v_weight,
+                                        w->gru_weight_ih, w->gru_weight_hh, w->mlp_1_weight,
+                                        w->mlp_3_weight, base, ws, C, D, Dm, st);
     if (e != cudaSuccess) return cuda_err(e);
     g_launches.fetch_add(1);
 
-    sfb::SAParams p{};
-    p.feats = reinterpret_cast<const float*>(feats);
-    p.feat_bstride = feat_batch_stride;
-    p.slots_in = slots_in;
-    p.slots_out = slots_out;
-    p.seg_mask = seg_mask;
-    p.ln_in_w = w->norm_inputs_weight; p.ln_in_b = w->norm_inputs_bias;
-    p.ln_q_w = w->project_q_0_weight;  p.ln_q_b = w->project_q_0_bias;
-    p.w_qk = w_qk; p.w_iv = w_iv;
-    p.w_hh = w->gru_weight_hh; p.b_ih = w->gru_bias_ih; p.b_hh = w->gru_bias_hh;
-    p.ln_m_w = w->mlp_0_weight; p.ln_m_b = w->mlp_0_bias;
-    p.w1 = w->mlp_1_weight; p.b1 = w->mlp_1_bias; p.w2 = w->mlp_3_weight; p.b2 = w->mlp_3_bias;
-    p.B = B; p.N = N; p.K = K; p.n_iter = n_iter; p.eps = eps;
-    p.rows_cta = plan.rows_cta; p.nstage = plan.nstage; p.lay = plan.lay;
-    p.prof = g_prof; p.prof_cap = g_prof_cap;
-    e = sfb::sa_launch(p, plan, C, 0, st);
-    if (e != cudaSuccess) return cuda_err(e);
-    g_launches.fetch_add(1);
+    auto H = [&](size_t off) { return reinterpret_cast<const __half*>(base + off); };
+    sfb::SAUpdateParams up{};
+    up.w.w_qk = H(ws.w_qk); up.w.w_iv = H(ws.w_iv); up.w.w_hh = H(ws.w_hh); up.w.w1 = H(ws.w1); up.w.w2 = H(ws.w2);
+    up.w.b_ih = w->gru_bias_ih; up.w.b_hh = w->gru_bias_hh; up.w.b1 = w->mlp_1_bias; up.w.b2 = w->mlp_3_bias;
+    up.w.ln_q_w = w->project_q_0_weight; up.w.ln_q_b = w->project_q_0_bias;
+    up.w.ln_m_w = w->mlp_0_weight; up.w.ln_m_b = w->mlp_0_bias;
+    up.partials = reinterpret_cast<const float*>(base + ws.partials);
+    up.xsum = reinterpret_cast<float*>(base + ws.xsum);
+    up.slots_out = slots_out;
+    up.qt = reinterpret_cast<__half*>(base + ws.qt);
+    up.B = B; up.N = N; up.K = K; up.nchunk = ws.nchunk; up.pstride = ws.pstride; up.eps = eps;
+
+    sfb::SAPassParams pp{};
+    pp.feats = reinterpret_cast<const float*>(feats);
+    pp.feat_bstride = feat_batch_stride;
+    pp.qt = up.qt;
+    pp.partials = reinterpret_cast<float*>(base + ws.partials);
+    pp.ln_w = w->norm_inputs_weight; pp.ln_b = w->norm_inputs_bias;
+    pp.B = B; pp.N = N; pp.K = K; pp.nchunk = ws.nchunk; pp.chunk_px = ws.chunk_px;
+    pp.pstride = ws.pstride; pp.n16 = ws.n16; pp.xhat_frames = ws.xhat_frames > 0 ? ws.xhat_frames : 1;
+    pp.prof = g_prof; pp.prof_cap = g_prof_cap;
+    { const char* dv = getenv("SFB_DBG"); pp.dbg = dv ? atoi(dv) : 0; }
+
+    for (int f0 = 0; f0 < B; f0 += chunk) {
+        const int nf = (B - f0) < chunk ? (B - f0) : chunk;
+        up.frame0 = f0; up.nframes = nf;
+        pp.frame0 = f0; pp.nframes = nf;
+        // q~ of the initial slots
+        up.do_update = 0; up.do_q = 1; up.first = 0; up.slots_prev = slots_in;
+        if ((e = sfb::sa_update_launch(up, C, di.sms, st)) != cudaSuccess) return cuda_err(e);
+        g_launches.fetch_add(1);
+        for (int it = 0; it < n_iter; ++it) {
+            const bool last = (it == n_iter - 1);
+            pp.xhat = (n_iter > 1) ? reinterpret_cast<__half*>(base + ws.xhat) : nullptr;
+            pp.seg_mask = last ? seg_mask : nullptr;
+            if ((e = sfb::sa_pass_launch(pp, C, it == 0, di.sms, di.smem_optin, st)) != cudaSuccess) return cuda_err(e);
+            g_launches.fetch_add(1);
+            up.do_update = 1; up.do_q = last ? 0 : 1; up.first = (it == 0);
+            up.slots_prev = (it == 0) ? slots_in : slots_out;
+            if ((e = sfb::sa_update_launch(up, C, di.sms, st)) != cudaSuccess) return cuda_err(e);
+            g_launches.fetch_add(1);
+        }
+    }
     return SFB_OK;
 }
 
@@ -160,27 +193,29 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
     if (workspace_bytes < sfb_rollout_workspace_bytes(Ds, d, F, w->num_layers)) return SFB_E_WORKSPACE;
     if (!aligned16(workspace)) return SFB_E_BAD_ALIGN;
     if (!w->in_proj_weight || !w->out_proj_weight) return SFB_E_NULL;
+    if (Ds % 64 || d % 64 || F % 64) return SFB_E_BAD_SHAPE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __half* dst = reinterpret_cast<__half*>(workspace);
     struct Job { const float* src; size_t n; };
     cudaError_t e;
-    auto run = [&](const float* src, size_t n) -> int {
+    auto run = [&](const float* src, int N_, int K_) -> int {
+        const size_t n = (size_t)N_ * K_;
         if (!src) return SFB_E_NULL;
-        e = sfb::ro_convert_launch(src, dst, n, st);
+        e = sfb::ro_pack_launch(src, dst, N_, K_, st);
         if (e != cudaSuccess) return cuda_err(e);
         g_launches.fetch_add(1);
         dst += n;
         return SFB_OK;
     };
     int rc;
-    if ((rc = run(w->in_proj_weight, (size_t)d * Ds))) return rc;
-    if ((rc = run(w->out_proj_weight, (size_t)Ds * d))) return rc;
+    if ((rc = run(w->in_proj_weight, d, Ds))) return rc;
+    if ((rc = run(w->out_proj_weight, Ds, d))) return rc;
     for (int l = 0; l < w->num_layers; ++l) {
         const sfb_ro_layer& ly = w->layers[l];
-        if ((rc = run(ly.self_attn_in_proj_weight, (size_t)3 * d * d))) return rc;
-        if ((rc = run(ly.self_attn_out_proj_weight, (size_t)d * d))) return rc;
-        if ((rc = run(ly.linear1_weight, (size_t)F * d))) return rc;
-        if ((rc = run(ly.linear2_weight, (size_t)d * F))) return rc;
+        if ((rc = run(ly.self_attn_in_proj_weight, 3 * d, d))) return rc;
+        if ((rc = run(ly.self_attn_out_proj_weight, d, d))) return rc;
+        if ((rc = run(ly.linear1_weight, F, d))) return rc;
+        if ((rc = run(ly.linear2_weight, d, F))) return rc;
     }
     return SFB_OK;
 }

@@ -1,0 +1,136 @@
+// LayerNorm-to-fp16 and per-(head, 16-query block) attention used by the rollout kernel.
+#pragma once
+#include "common.cuh"
+
+namespace sfb {
+
+static constexpr int RO_WARPS = 8;            // consumer warps
+static constexpr int RO_THREADS = RO_WARPS * 32;
+static constexpr float RO_LN_EPS = 1e-5f;
+
+// LayerNorm rows [0, L) of h (fp32, stride d) -> fp16 rows of `out` (stride ldo); rows [L, Lp) = 0
+template <int DMODEL>
+__device__ __forceinline__ void ln_to_half(const float* h, __half* out, int ldo, int L, int Lp,
+                                           const float* __restrict__ gw, const float* __restrict__ gb,
+                                           int warp, int lane) {
+    constexpr int PER = DMODEL / 32;
+    float gmm[PER], bta[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { gmm[i] = gw[lane + 32 * i]; bta[i] = gb[lane + 32 * i]; }
+    for (int r = warp; r < Lp; r += RO_WARPS) {
+        if (r < L) {
+            float v[PER];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { v[i] = h[r * DMODEL + lane + 32 * i]; s += v[i]; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mu = s * (1.f / DMODEL);
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { v[i] -= mu; q = fmaf(v[i], v[i], q); }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(q * (1.f / DMODEL) + RO_LN_EPS);
+#pragma unroll
+            for (int i = 0; i < PER; ++i)
+                out[r * ldo + lane + 32 * i] = __float2half_rn(fmaf(v[i] * rstd, gmm[i], bta[i]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) out[r * ldo + lane + 32 * i] = __float2half_rn(0.f);
+        }
+    }
+}
+
+// One (head, 16-query block) of softmax(Q K^T / sqrt(dh)) V.  Q/K/V live in `buf` (fp16, stride
+// ldb) at column offsets qcol/kcol/vcol; the result overwrites the Q block it came from.
+template <int DH, int NKB>
+__device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qcol, int kcol,
+                                           int vcol, int L, int nkb, float sm_scale_log2, int lane) {
+    const int g = lane >> 2, t4 = lane & 3;
+    const uint32_t b_u32 = smem_u32(buf);
+    uint32_t qf[DH / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+        const int row = 16 * mb + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4(qf[ks], b_u32 + (uint32_t)(row * ldb + qcol + 16 * ks + (lane >> 4) * 8) * 2u);
+    }
+    float s[NKB][4];
+#pragma unroll
+    for (int nb = 0; nb < NKB; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
+#pragma unroll
+    for (int nb = 0; nb < NKB; nb += 2) {
+        if (nb < nkb) {
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks) {
+                uint32_t kf[4];
+                const int row = 8 * nb + (lane & 7) + (lane >> 4) * 8;
+                ldsm_x4(kf, b_u32 + (uint32_t)(row * ldb + kcol + 16 * ks + ((lane >> 3) & 1) * 8) * 2u);
+                mma_f16(s[nb], qf[ks], kf[0], kf[1]);
+                mma_f16(s[nb + 1], qf[ks], kf[2], kf[3]);
+            }
+        }
+    }
+    // softmax over keys (rows g and g+8); keys >= L are masked
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < NKB; ++nb) {
+        if (nb < nkb) {
+            const int c = 8 * nb + 2 * t4;
+            s[nb][0] = (c < L) ? s[nb][0] * sm_scale_log2 : -INFINITY;
+            s[nb][1] = (c + 1 < L) ? s[nb][1] * sm_scale_log2 : -INFINITY;
+            s[nb][2] = (c < L) ? s[nb][2] * sm_scale_log2 : -INFINITY;
+            s[nb][3] = (c + 1 < L) ? s[nb][3] * sm_scale_log2 : -INFINITY;
+            m0 = fmaxf(m0, fmaxf(s[nb][0], s[nb][1]));
+            m1 = fmaxf(m1, fmaxf(s[nb][2], s[nb][3]));
+        }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pf[NKB][2];
+#pragma unroll
+    for (int nb = 0; nb < NKB; ++nb) {
+        if (nb < nkb) {
+            const float e0 = exp2f(s[nb][0] - m0), e1 = exp2f(s[nb][1] - m0);
+            const float e2 = exp2f(s[nb][2] - m1), e3 = exp2f(s[nb][3] - m1);
+            const __half2 h01 = __floats2half2_rn(e0, e1), h23 = __floats2half2_rn(e2, e3);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            l0 += f01.x + f01.y; l1 += f23.x + f23.y;      // normaliser from the rounded values
+            pf[nb][0] = *reinterpret_cast<const uint32_t*>(&h01);
+            pf[nb][1] = *reinterpret_cast<const uint32_t*>(&h23);
+        } else {
+            pf[nb][0] = pf[nb][1] = 0u;
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // O = P V
+    float o[DH / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < DH / 8; ++nb) { o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < NKB / 2; ++kk) {
+        if (2 * kk < nkb) {
+            const uint32_t a[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
+#pragma unroll
+            for (int nb = 0; nb < DH / 8; nb += 2) {
+                uint32_t vf[4];
+                const int row = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+                ldsm_x4_t(vf, b_u32 + (uint32_t)(row * ldb + vcol + 8 * nb + (lane >> 4) * 8) * 2u);
+                mma_f16(o[nb], a, vf[0], vf[1]);
+                mma_f16(o[nb + 1], a, vf[2], vf[3]);
+            }
+        }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    __syncwarp();   // every lane has its Q fragments; the Q block may now be overwritten
+#pragma unroll
+    for (int nb = 0; nb < DH / 8; ++nb) {
+        const int col = qcol + 8 * nb + 2 * t4;
+        *reinterpret_cast<__half2*>(buf + (16 * mb + g) * ldb + col) = __floats2half2_rn(o[nb][0] * i0, o[nb][1] * i0);
+        *reinterpret_cast<__half2*>(buf + (16 * mb + g + 8) * ldb + col) = __floats2half2_rn(o[nb][2] * i1, o[nb][3] * i1);
+    }
+}
+
+}  // namespace sfb

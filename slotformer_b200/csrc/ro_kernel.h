@@ -10,16 +10,16 @@ namespace sfb {
 static constexpr int RO_MAX_LAYERS = 16;
 
 struct ROLayer {
-    const __half *wqkv, *wo, *w1, *w2;                    // fp16 operand copies (workspace)
+    const __half *wqkv, *wo, *w1, *w2;                    // packed fp16 panels (workspace)
     const float *bqkv, *bo, *b1, *b2, *ln1w, *ln1b, *ln2w, *ln2b;   // fp32 originals
 };
 
 struct ROParams {
     const float* hist;   // [B][T_h*K][Ds]
     float* pred;         // [B][pred_len*K][Ds]
-    const __half* w_in;  // [d][Ds]
+    const __half* w_in;  // packed [d][Ds]
     const float* b_in;
-    const __half* w_out; // [Ds][d]
+    const __half* w_out; // packed [Ds][d]
     const float* b_out;
     const float* pe;     // [pe_tokens][d]
     int B, hist_tokens, K, Ds, d, F, heads, layers, pred_len, mode, cond_tokens, pe_tokens;
@@ -27,14 +27,16 @@ struct ROParams {
     int fc;              // FFN hidden chunk (columns)
     int lmax;            // max window tokens over the rollout
     int lda, ldb;        // row strides (halves) of the fp16 activation buffers
-    uint32_t off_h, off_a, off_b;   // shared-memory byte offsets
-    unsigned long long* prof;       // optional timeline buffer (debug), CTA 0 / thread 0
+    int ln_smem;         // LayerNorm parameters staged in shared memory
+    int nstage;          // weight-panel ring depth
+    uint32_t off_h, off_a, off_b, off_bars, off_ring, off_ln;   // shared-memory byte offsets
+    unsigned long long* prof;       // optional timeline buffer (debug)
     int prof_cap;
     ROLayer layer[RO_MAX_LAYERS];
 };
 
-// fp32 -> fp16 copy of `n` elements
-cudaError_t ro_convert_launch(const float* src, __half* dst, size_t n, cudaStream_t st);
+// fp32 [N][Kd] -> fp16 64x64 panels, 128B-swizzled (N, Kd multiples of 64)
+cudaError_t ro_pack_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st);
 // chooses hg / fc / buffer layout; returns 0 or -1 if the shape cannot be kept on chip
 int ro_plan(ROParams* p, int smem_limit, size_t* smem_bytes);
 cudaError_t ro_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st);

@@ -1,48 +1,70 @@
 // Internal interface between the C ABI (capi.cu) and the Slot Attention kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stddef.h>
 
 namespace sfb {
 
-// byte offsets of the shared-memory regions of sa_forward_kernel (computed on the host)
-struct SALayout {
-    uint32_t slab, ring, red, rs_buf, qfrag, s_cur, gates, colsum_buf, colsum_w, rs_x, xs_part,
-        lnw, bars;
+// slot-update weights as packed fp16 hi/lo panel pairs (built once per call by sa_prep):
+// pair (nb, kb) of a [N][Kd] matrix = 64x64 hi panel then 64x64 lo panel, 128B-swizzled rows
+struct SAWeightsDev {
+    const __half* w_qk;   // [C][D]   scale*log2e * (Wq^T Wk)^T : q~ = LNq(S) W_qk^T
+    const __half* w_iv;   // [3D][C]  W_ih Wv
+    const __half* w_hh;   // [3D][D]
+    const __half* w1;     // [Dm][D]
+    const __half* w2;     // [D][Dm]
+    const float *b_ih, *b_hh, *b1, *b2;
+    const float *ln_q_w, *ln_q_b, *ln_m_w, *ln_m_b;
 };
 
-struct SAPlan {
-    SALayout lay;
-    int cluster_size;
-    int rows_cta;   // pixels owned by one CTA (multiple of 128)
-    int nstage;     // TMA ring depth
-    size_t smem_bytes;
+// workspace carve-up (byte offsets), computed by sa_workspace_layout
+struct SAWorkspace {
+    size_t w_qk, w_iv, w_hh, w1, w2;   // each: hi then lo
+    size_t qt;         // [B][2][8][C] fp16
+    size_t partials;   // [B][nchunk][pstride] fp32
+    size_t xsum;       // [B][C] fp32
+    size_t xhat;       // [xhat_frames][N16/16][16*C] fp16 (swizzled 16-pixel tiles)
+    size_t total;
+    int nchunk, chunk_px, pstride, n16, xhat_frames;
 };
 
-struct SAParams {
+struct SAPassParams {
     const float* feats;
-    long long feat_bstride;   // elements between consecutive frames
-    const float* slots_in;
-    float* slots_out;
-    float* seg_mask;          // nullable
-    const float *ln_in_w, *ln_in_b, *ln_q_w, *ln_q_b;
-    const float* w_qk;        // [C][D]  folded, includes scale*log2(e)
-    const float* w_iv;        // [3D][C] folded W_ih Wv
-    const float *w_hh, *b_ih, *b_hh;
-    const float *ln_m_w, *ln_m_b, *w1, *b1, *w2, *b2;
-    int B, N, K, n_iter;
-    float eps;
-    int rows_cta, nstage;
-    SALayout lay;
-    unsigned long long* prof;   // optional timeline buffer (debug), cluster 0 / CTA 0 / thread 0
+    long long feat_bstride;    // elements between frames
+    __half* xhat;              // nullable when there is no later pass
+    const __half* qt;          // [B][2][8][C]
+    float* partials;
+    float* seg_mask;           // nullable; written only by the last pass
+    const float *ln_w, *ln_b;  // norm_inputs
+    int B, N, K, nchunk, chunk_px, pstride, n16, xhat_frames;
+    int frame0;                // first frame of this launch (chunked scheduling)
+    int nframes;               // frames in this launch
+    unsigned long long* prof;
     int prof_cap;
+    int dbg;                   // debug switches (SFB_DBG env): 1 = no proxy fence, 2 = no x^ store, 4 = skip LN+MMA work
 };
 
-int sa_plan(int N, int C, int D, int DM, int cluster_size, int smem_limit, SAPlan* plan);
-cudaError_t sa_launch(const SAParams& p, const SAPlan& plan, int C, int max_clusters_hint, cudaStream_t st);
-int sa_max_clusters(int C, int cluster_size);
-cudaError_t sa_fold_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,
-                           float* w_qk, float* w_iv, int C, int D, cudaStream_t st);
+struct SAUpdateParams {
+    SAWeightsDev w;
+    const float* partials;
+    float* xsum;               // [B][C]; written when first != 0
+    const float* slots_prev;   // [B][K][D] state before this update (slots_in or slots_out)
+    float* slots_out;          // [B][K][D]
+    __half* qt;                // [B][2][8][C]; written when do_q != 0
+    int B, N, K, nchunk, pstride;
+    int frame0, nframes;
+    int do_update, do_q, first;
+    float eps;
+};
+
+void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, int n_iter, SAWorkspace* ws);
+cudaError_t sa_prep_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,
+                           const float* w_hh, const float* w1, const float* w2, char* ws_base,
+                           const SAWorkspace& ws, int C, int D, int DM, cudaStream_t st);
+cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, int smem_limit, cudaStream_t st);
+cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st);
+bool sa_shape_supported(int C, int D, int DM);
 
 }  // namespace sfb

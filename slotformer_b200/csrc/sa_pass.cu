@@ -1,0 +1,426 @@
+// Slot Attention forward for sm_100a: batched streaming passes + batched slot updates.
+//
+// Replaces reference SlotAttention.forward (base_slots/models/savi.py:56-102) and
+// SlotAttentionWMask.forward (base_slots/models/steve.py:19-73).
+//
+// Design (v0 -- one cluster per frame -- was latency bound by ~11 cluster
+// syncs per frame, see profiles/r1_v0_timeline.txt):
+//   * The K/V projections are never materialised.  With x^ = LN(x):
+//        logits[n,m] = scale * <x^[n] Wk^T, q[m]>  = <x^[n], q~[m]>,   q~ = LNq(S) W_qk^T
+//        updates[m]  = sum_n w[n,m] (x^[n] Wv^T)    = (sum_n w[n,m] x^[n]) Wv^T
+//     so an iteration needs only x^ (N x C) and two K x C matrices; W_qk = scale*log2e*(Wq^T Wk)
+//     and W_iv = W_ih Wv are folded once per call (sa_prep_kernel).
+//   * sa_pass_kernel<FIRST>: persistent CTAs stream (frame, pixel-chunk) items.  Every warp runs
+//     its own TMA pipeline (1-D bulk copies of 16-pixel tiles into a private mbarrier ring):
+//     LayerNorm in place -> fp16 x^ tile (swizzled for ldmatrix) -> logits on tensor cores
+//     (mma.sync, q~ split hi+lo) -> softmax over the slots with quad shuffles -> movmatrix
+//     transpose -> U^T[C x 8] += x^T P on tensor cores.  The x^ tile is also written (as the
+//     ready-made smem image) to a ring in global memory, so later iterations
+//     (sa_pass_kernel<NEXT>) re-read 2 B/element (L2 resident when the ring is small) instead of
+//     4 B/element from HBM.  +eps is applied analytically:
+//        sum_n (a+eps) x^ = sum_n a x^ + eps sum_n x^ ,   sum_n (a+eps) = sum_n a + N eps.
+//   * sa_update_kernel: GRU + residual MLP + next q~ for 16 rows (2 frames) per warp, batched
+//     over all frames, tensor cores with 3-term fp16 splitting (hi*hi + lo*hi + hi*lo ~ fp32).
+#include "common.cuh"
+#include "sa_kernel.h"
+
+namespace sfb {
+
+static constexpr int PASS_WARPS = 8;
+static constexpr int PASS_THREADS = PASS_WARPS * 32;
+static constexpr float SA_PSCALE = 1024.f;   // probabilities are stored as fp16(1024 * a)
+static constexpr float LN_EPS = 1e-5f;
+
+bool sa_shape_supported(int C, int D, int DM) {
+    return (C == 128 && D == 128 && DM == 256) || (C == 192 && D == 192 && DM == 384);
+}
+
+// ============================================================================================
+// streaming pass
+// ============================================================================================
+template <int C, bool FIRST>
+struct PassCfg {
+    static constexpr int KS = C / 16;
+    static constexpr int ROWB = C * 2;                       // x^ row bytes
+    static constexpr int XT_BYTES = 16 * ROWB;               // x^ tile (16 px) bytes
+    static constexpr int STAGE_BYTES = FIRST ? 16 * C * 4 : XT_BYTES;
+    static constexpr int NST = FIRST ? (C == 128 ? 3 : 2) : (C == 128 ? 6 : 4);
+    static constexpr int NQB = (C == 128) ? 2 : 1;           // q~ buffers (double-buffered if room)
+    static constexpr int NREG = KS * 4;
+    static constexpr int OFF_STAGES = 0;
+    static constexpr int OFF_RED = PASS_WARPS * NST * STAGE_BYTES;
+    static constexpr int RED_BYTES = 4 * NREG * 32 * 4;
+    static constexpr int OFF_QF = OFF_RED + RED_BYTES;
+    static constexpr int QF_BYTES = 2 * 8 * C * 2;           // hi + lo
+    static constexpr int OFF_LN = OFF_QF + NQB * QF_BYTES;
+    static constexpr int OFF_CSW = OFF_LN + 2 * C * 4;
+    static constexpr int OFF_BARS = OFF_CSW + 8 * 8 * 4;
+    static constexpr int SMEM = OFF_BARS + PASS_WARPS * NST * 8;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int C, bool FIRST>
+__global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassParams p) {
+    using Cfg = PassCfg<C, FIRST>;
+    constexpr int KS = Cfg::KS, ROWB = Cfg::ROWB, XT_BYTES = Cfg::XT_BYTES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES, NST = Cfg::NST, NREG = Cfg::NREG, NQB = Cfg::NQB;
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* my_stages = smem + Cfg::OFF_STAGES + warp * NST * STAGE_BYTES;
+    float* red = reinterpret_cast<float*>(smem + Cfg::OFF_RED);
+    __half* qf = reinterpret_cast<__half*>(smem + Cfg::OFF_QF);
+    float* lng = reinterpret_cast<float*>(smem + Cfg::OFF_LN);
+    float* lnb = lng + C;
+    float* colsum_w = reinterpret_cast<float*>(smem + Cfg::OFF_CSW);
+    uint64_t* my_bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS) + warp * NST;
+
+    const int N = p.N, K = p.K;
+    const int items = p.nframes * p.nchunk;
+    const int nbw = p.chunk_px >> 7;                 // 16-px tiles per warp per item
+    const int tiles_chunk = p.chunk_px >> 4;
+    const int tiles_frame = p.nchunk * tiles_chunk;
+    const int my_items = (items > (int)blockIdx.x) ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t total_tiles = (uint32_t)my_items * nbw;
+
+    if (lane == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(&my_bars[s], 1);
+        fence_mbar_init();
+    }
+    if (FIRST) for (int i = tid; i < C; i += PASS_THREADS) { lng[i] = p.ln_w[i]; lnb[i] = p.ln_b[i]; }
+    __syncthreads();
+    if (my_items == 0) return;
+
+    const uint64_t pol = FIRST ? l2_policy_evict_first() : l2_policy_evict_last();
+
+    auto issue = [&](uint32_t n) {
+        if (n < total_tiles && lane == 0) {
+            const int il = n / nbw, j = n % nbw;
+            const int item = (int)blockIdx.x + il * (int)gridDim.x;
+            const int fl = item / p.nchunk, c = item % p.nchunk;
+            const int f = p.frame0 + fl;
+            const int tb = c * tiles_chunk + warp + PASS_WARPS * j;
+            const int px0 = tb * 16;
+            int nvalid = N - px0;
+            nvalid = nvalid < 0 ? 0 : (nvalid > 16 ? 16 : nvalid);
+            const int s = n % NST;
+            if (nvalid > 0) {
+                const void* src;
+                uint32_t bytes;
+                if (FIRST) {
+                    src = p.feats + (size_t)f * p.feat_bstride + (size_t)px0 * C;
+                    bytes = (uint32_t)nvalid * C * 4;
+                } else {
+                    src = p.xhat + ((size_t)(f % p.xhat_frames) * tiles_frame + tb) * (16 * C);
+                    bytes = XT_BYTES;
+                }
+                mbar_arrive_expect_tx(&my_bars[s], bytes);
+                bulk_g2s(my_stages + s * STAGE_BYTES, src, bytes, &my_bars[s], pol);
+            } else {
+                mbar_arrive(&my_bars[s]);
+            }
+        }
+    };
+    auto load_qf = [&](int il, int buf, bool async) {
+        const int item = (int)blockIdx.x + il * (int)gridDim.x;
+        const int f = p.frame0 + item / p.nchunk;
+        const uint4* src = reinterpret_cast<const uint4*>(p.qt + (size_t)f * (2 * 8 * C));
+        uint4* dst = reinterpret_cast<uint4*>(qf + (size_t)buf * (2 * 8 * C));
+        for (int i = tid; i < Cfg::QF_BYTES / 16; i += PASS_THREADS) {
+            if (async) cp_async16(dst + i, src + i);
+            else dst[i] = __ldg(src + i);
+        }
+        if (async) cp_async_commit();
+    };
+
+    const int g = lane >> 2, t4 = lane & 3;
+    const int pxi = lane >> 3, ch8 = lane & 7;
+
+#pragma unroll 1
+    for (uint32_t n0 = 0; n0 + 1 < (uint32_t)NST; ++n0) issue(n0);
+    load_qf(0, 0, false);
+    __syncthreads();
+
+    uint32_t n = 0;
+#pragma unroll 1
+    for (int il = 0; il < my_items; ++il) {
+        const int item = (int)blockIdx.x + il * (int)gridDim.x;
+        const int fl = item / p.nchunk, chunk = item % p.nchunk;
+        const int f = p.frame0 + fl;
+        const __half* qh = qf + (size_t)((NQB == 2) ? (il & 1) : 0) * (2 * 8 * C);
+        const __half* ql = qh + 8 * C;
+        if (NQB == 2 && il + 1 < my_items) load_qf(il + 1, (il + 1) & 1, true);
+
+        uint32_t bq_hi[KS][2], bq_lo[KS][2];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int c0 = 16 * ks + 2 * t4;
+            bq_hi[ks][0] = *reinterpret_cast<const uint32_t*>(qh + g * C + c0);
+            bq_hi[ks][1] = *reinterpret_cast<const uint32_t*>(qh + g * C + c0 + 8);
+            bq_lo[ks][0] = *reinterpret_cast<const uint32_t*>(ql + g * C + c0);
+            bq_lo[ks][1] = *reinterpret_cast<const uint32_t*>(ql + g * C + c0 + 8);
+        }
+        float uacc[KS][4];
+#pragma unroll
+        for (int cb = 0; cb < KS; ++cb) { uacc[cb][0] = uacc[cb][1] = uacc[cb][2] = uacc[cb][3] = 0.f; }
+        float cs0 = 0.f, cs1 = 0.f;
+        float xs[C / 32][4];
+#pragma unroll
+        for (int i = 0; i < C / 32; ++i) { xs[i][0] = xs[i][1] = xs[i][2] = xs[i][3] = 0.f; }
+        const bool s0ok = (2 * t4) < K, s1ok = (2 * t4 + 1) < K;
+
+#pragma unroll 1
+        for (int j = 0; j < nbw; ++j, ++n) {
+            issue(n + NST - 1);
+            const int s = n % NST;
+            unsigned char* stg = my_stages + s * STAGE_BYTES;
+            const int tb = chunk * tiles_chunk + warp + PASS_WARPS * j;
+            const int px0 = tb * 16;
+            int nvalid = N - px0;
+            nvalid = nvalid < 0 ? 0 : (nvalid > 16 ? 16 : nvalid);
+            mbar_wait(&my_bars[s], (n / NST) & 1);
+            if (nvalid > 0 && !(p.dbg & 4)) {
+                if (FIRST) {
+                    // ---- LayerNorm 16 pixels in place: fp32 rows -> swizzled fp16 x^ tile ----
+                    // (x^ rows 8h..8h+7 land on raw rows 4h..4h+3, which are already in registers)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float4 v[2][C / 32];
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int row = 8 * hf + 4 * rr + pxi;
+                            const float* tp = reinterpret_cast<const float*>(stg) + row * C + 4 * ch8;
+#pragma unroll
+                            for (int i = 0; i < C / 32; ++i)
+                                v[rr][i] = (row < nvalid) ? *reinterpret_cast<const float4*>(tp + 32 * i)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int row = 8 * hf + 4 * rr + pxi;
+                            const bool valid = row < nvalid;
+                            float sm = 0.f;
+#pragma unroll
+                            for (int i = 0; i < C / 32; ++i) sm += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
+                            sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+                            sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                            sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+                            const float mu = sm * (1.f / C);
+                            float qv = 0.f;
+#pragma unroll
+                            for (int i = 0; i < C / 32; ++i) {
+                                v[rr][i].x -= mu; v[rr][i].y -= mu; v[rr][i].z -= mu; v[rr][i].w -= mu;
+                                qv = fmaf(v[rr][i].x, v[rr][i].x, qv); qv = fmaf(v[rr][i].y, v[rr][i].y, qv);
+                                qv = fmaf(v[rr][i].z, v[rr][i].z, qv); qv = fmaf(v[rr][i].w, v[rr][i].w, qv);
+                            }
+                            qv += __shfl_xor_sync(0xffffffffu, qv, 1);
+                            qv += __shfl_xor_sync(0xffffffffu, qv, 2);
+                            qv += __shfl_xor_sync(0xffffffffu, qv, 4);
+                            const float rstd = valid ? rsqrtf(qv * (1.f / C) + LN_EPS) : 0.f;
+                            unsigned char* rowp = stg + row * ROWB + (ch8 & 1) * 8;
+#pragma unroll
+                            for (int i = 0; i < C / 32; ++i) {
+                                const float4 gm = *reinterpret_cast<const float4*>(lng + 4 * ch8 + 32 * i);
+                                const float4 bt = *reinterpret_cast<const float4*>(lnb + 4 * ch8 + 32 * i);
+                                const float y0 = valid ? fmaf(v[rr][i].x * rstd, gm.x, bt.x) : 0.f;
+                                const float y1 = valid ? fmaf(v[rr][i].y * rstd, gm.y, bt.y) : 0.f;
+                                const float y2 = valid ? fmaf(v[rr][i].z * rstd, gm.z, bt.z) : 0.f;
+                                const float y3 = valid ? fmaf(v[rr][i].w * rstd, gm.w, bt.w) : 0.f;
+                                xs[i][0] += y0; xs[i][1] += y1; xs[i][2] += y2; xs[i][3] += y3;
+                                const int chk = ((ch8 >> 1) + 4 * i) ^ (row & 7);
+                                uint2 pk; pk.x = pack_h2(y0, y1); pk.y = pack_h2(y2, y3);
+                                *reinterpret_cast<uint2*>(rowp + chk * 16) = pk;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (p.xhat != nullptr && !(p.dbg & 2)) {
+                        // ready-made smem image of the tile -> x^ ring in global memory
+                        uint4* dst = reinterpret_cast<uint4*>(
+                            p.xhat + ((size_t)(f % p.xhat_frames) * tiles_frame + tb) * (16 * C));
+                        const uint4* srcv = reinterpret_cast<const uint4*>(stg);
+#pragma unroll
+                        for (int q = 0; q < XT_BYTES / 512; ++q) dst[lane + 32 * q] = srcv[lane + 32 * q];
+                    }
+                }
+                const uint32_t tile_u32 = smem_u32(stg);
+                // ---- logits: 16 pixels x 8 slots, log2 domain (scale folded into q~) ----
+                float lgA[4] = {0.f, 0.f, 0.f, 0.f}, lgB[4] = {0.f, 0.f, 0.f, 0.f};
+                {
+                    const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const uint32_t rowa = tile_u32 + row * ROWB;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks += 2) {
+                        uint32_t a0[4], a1[4];
+                        ldsm_x4(a0, rowa + (((2 * ks + (lane >> 4)) ^ (row & 7)) << 4));
+                        ldsm_x4(a1, rowa + (((2 * ks + 2 + (lane >> 4)) ^ (row & 7)) << 4));
+                        mma_f16(lgA, a0, bq_hi[ks][0], bq_hi[ks][1]);
+                        mma_f16(lgB, a0, bq_lo[ks][0], bq_lo[ks][1]);
+                        mma_f16(lgA, a1, bq_hi[ks + 1][0], bq_hi[ks + 1][1]);
+                        mma_f16(lgB, a1, bq_lo[ks + 1][0], bq_lo[ks + 1][1]);
+                    }
+                }
+                float lg[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) lg[e] = lgA[e] + lgB[e];
+                const int pxa = px0 + g, pxb = pxa + 8;
+                float pa0, pa1, pb0, pb1;
+                {
+                    float ma = fmaxf(s0ok ? lg[0] : -INFINITY, s1ok ? lg[1] : -INFINITY);
+                    float mb = fmaxf(s0ok ? lg[2] : -INFINITY, s1ok ? lg[3] : -INFINITY);
+                    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+                    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+                    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+                    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+                    const float ea0 = s0ok ? exp2f(lg[0] - ma) : 0.f, ea1 = s1ok ? exp2f(lg[1] - ma) : 0.f;
+                    const float eb0 = s0ok ? exp2f(lg[2] - mb) : 0.f, eb1 = s1ok ? exp2f(lg[3] - mb) : 0.f;
+                    float sa = ea0 + ea1, sb = eb0 + eb1;
+                    sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                    sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+                    const float ia = (pxa < N) ? __fdividef(1.f, sa) : 0.f;
+                    const float ib = (pxb < N) ? __fdividef(1.f, sb) : 0.f;
+                    pa0 = ea0 * ia; pa1 = ea1 * ia; pb0 = eb0 * ib; pb1 = eb1 * ib;
+                }
+                if (p.seg_mask != nullptr) {
+                    float* mk = p.seg_mask + (size_t)f * K * N;
+                    if (pxa < N) {
+                        if (s0ok) mk[(size_t)(2 * t4) * N + pxa] = pa0;
+                        if (s1ok) mk[(size_t)(2 * t4 + 1) * N + pxa] = pa1;
+                    }
+                    if (pxb < N) {
+                        if (s0ok) mk[(size_t)(2 * t4) * N + pxb] = pb0;
+                        if (s1ok) mk[(size_t)(2 * t4 + 1) * N + pxb] = pb1;
+                    }
+                }
+                const __half2 ha = __floats2half2_rn(pa0 * SA_PSCALE, pa1 * SA_PSCALE);
+                const __half2 hb = __floats2half2_rn(pb0 * SA_PSCALE, pb1 * SA_PSCALE);
+                {
+                    const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+                    cs0 += fa.x + fb.x; cs1 += fa.y + fb.y;   // column sums from the ROUNDED values
+                }
+                const uint32_t b0 = movmatrix_t(*reinterpret_cast<const uint32_t*>(&ha));
+                const uint32_t b1 = movmatrix_t(*reinterpret_cast<const uint32_t*>(&hb));
+                // ---- aggregation U^T[16 ch x 8 slots] += x^T[16 ch x 16 px] * P[16 px x 8 slots] ----
+                {
+                    const int row = (lane & 7) + (lane >> 4) * 8;
+                    const uint32_t rowa = tile_u32 + row * ROWB;
+#pragma unroll
+                    for (int cb = 0; cb < KS; cb += 2) {
+                        uint32_t a0[4], a1[4];
+                        ldsm_x4_t(a0, rowa + (((2 * cb + ((lane >> 3) & 1)) ^ (row & 7)) << 4));
+                        ldsm_x4_t(a1, rowa + (((2 * cb + 2 + ((lane >> 3) & 1)) ^ (row & 7)) << 4));
+                        mma_f16(uacc[cb], a0, b0, b1);
+                        mma_f16(uacc[cb + 1], a1, b0, b1);
+                    }
+                }
+            }
+            if (!(p.dbg & 1)) fence_proxy_async();   // generic-proxy accesses of this stage precede its next TMA fill
+            __syncwarp();
+        }
+
+        // ================= item end: reduce the 8 warps' partials, write them out =================
+        float* part = p.partials + ((size_t)f * p.nchunk + chunk) * p.pstride;
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+        if (lane < 4) { colsum_w[warp * 8 + 2 * lane] = cs0; colsum_w[warp * 8 + 2 * lane + 1] = cs1; }
+        if (FIRST) {
+#pragma unroll
+            for (int i = 0; i < C / 32; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = xs[i][e];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    xs[i][e] = a;
+                }
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < C / 32; ++i)
+                    *reinterpret_cast<float4*>(red + warp * C + 4 * lane + 32 * i) =
+                        make_float4(xs[i][0], xs[i][1], xs[i][2], xs[i][3]);
+            }
+            __syncthreads();
+            if (tid < C) {
+                float a = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < PASS_WARPS; ++w8) a += red[w8 * C + tid];
+                part[8 * C + 8 + tid] = a;
+            }
+            __syncthreads();
+        }
+        {
+            auto put = [&](int slot) {
+#pragma unroll
+                for (int cb = 0; cb < KS; ++cb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) red[(slot * NREG + cb * 4 + e) * 32 + lane] = uacc[cb][e];
+            };
+            auto add = [&](int slot) {
+#pragma unroll
+                for (int cb = 0; cb < KS; ++cb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) uacc[cb][e] += red[(slot * NREG + cb * 4 + e) * 32 + lane];
+            };
+            if (warp >= 4) put(warp - 4);
+            __syncthreads();
+            if (warp < 4) add(warp);
+            if (warp == 2 || warp == 3) put(warp);
+            __syncthreads();
+            if (warp < 2) add(2 + warp);
+            if (warp == 1) put(1);
+            __syncthreads();
+            if (warp == 0) {
+                add(1);
+#pragma unroll
+                for (int cb = 0; cb < KS; ++cb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 16 * cb + g + 8 * (e >> 1);
+                        const int slot = 2 * t4 + (e & 1);
+                        part[slot * C + c] = uacc[cb][e];
+                    }
+            } else if (warp == 1 && lane < 8) {
+                float a = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < PASS_WARPS; ++w8) a += colsum_w[w8 * 8 + lane];
+                part[8 * C + lane] = a;
+            }
+        }
+        if (NQB == 2) {
+            cp_async_wait_all();
+        } else if (il + 1 < my_items) {
+            __syncthreads();                 // everyone finished reading the single q~ buffer
+            load_qf(il + 1, 0, false);
+        }
+        __syncthreads();
+    }
+}
+
+template <int C, bool FIRST>
+static cudaError_t pass_launch_t(const SAPassParams& p, int sms, cudaStream_t st) {
+    using Cfg = PassCfg<C, FIRST>;
+    auto kern = sa_pass_kernel<C, FIRST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    const int items = p.nframes * p.nchunk;
+    const int grid = items < sms ? items : sms;
+    kern<<<grid, PASS_THREADS, Cfg::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, int smem_limit, cudaStream_t st) {
+    (void)smem_limit;
+    if (C == 128) return first ? pass_launch_t<128, true>(p, sms, st) : pass_launch_t<128, false>(p, sms, st);
+    return first ? pass_launch_t<192, true>(p, sms, st) : pass_launch_t<192, false>(p, sms, st);
+}
+
+}  // namespace sfb

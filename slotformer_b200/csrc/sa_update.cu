@@ -1,0 +1,457 @@
+// Slot Attention: batched slot update (GRU + residual MLP + next q~), weight preparation and
+// workspace layout.  Reference: base_slots/models/savi.py:80 (project_q), :95-100 (GRUCell, MLP).
+//
+// One CTA updates 16*NMB slot rows (2*NMB frames x 8 padded slots).  The fp16 hi/lo weight panels
+// (64 x 64, 128B-swizzled, prepared once per call by sa_prep_kernel) are streamed by a producer
+// warp with TMA bulk copies through an mbarrier ring; 8 math warps each own 8 of a panel's 64
+// output columns for all rows.  Every product uses 3-term fp16 splitting
+// (A_hi W_hi + A_lo W_hi + A_hi W_lo), which keeps the update at fp32-level accuracy on tensor
+// cores.  The first version of this kernel read the weights straight from L2 per warp and
+// was latency bound (207 us per launch, profiles/r1_sa_v1_launches.txt).
+#include "common.cuh"
+#include "sa_kernel.h"
+
+namespace sfb {
+
+static constexpr float SA_PSCALE = 1024.f;   // must match sa_pass.cu
+static constexpr float LN_EPS = 1e-5f;
+static constexpr int UPD_WARPS = 8;
+static constexpr int UPD_THREADS = UPD_WARPS * 32;
+static constexpr int PAIR_HALVES = 2 * 64 * 64;     // hi panel + lo panel
+static constexpr int PAIR_BYTES = PAIR_HALVES * 2;
+
+// ============================================================================================
+// weight preparation: fold, split into fp16 hi/lo, pack into swizzled 64x64 panel pairs
+// ============================================================================================
+__device__ __forceinline__ void store_packed(__half* dst, int kpt, int n, int k, float v) {
+    const int nb = n >> 6, r = n & 63, kb = k >> 6, kk = k & 63;
+    __half* pair = dst + ((size_t)nb * kpt + kb) * PAIR_HALVES;
+    const int off = r * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
+    const __half h = __float2half_rn(v);
+    pair[off] = h;
+    pair[64 * 64 + off] = __float2half_rn(v - __half2float(h));
+}
+
+__global__ void sa_prep_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
+                               const float* __restrict__ wv, const float* __restrict__ w_ih,
+                               const float* __restrict__ w_hh, const float* __restrict__ w1,
+                               const float* __restrict__ w2, __half* qk, __half* iv, __half* hh,
+                               __half* p1, __half* p2, int C, int D, int DM, float qscale) {
+    const int n_qk = C * D, n_iv = 3 * D * C, n_hh = 3 * D * D, n_1 = DM * D, n_2 = D * DM;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_qk) {                       // W_qk[c][e] = qscale * sum_d Wq[d][e] Wk[d][c]
+        const int c = idx / D, e = idx % D;
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc = fmaf(wq[d * D + e], wk[d * C + c], acc);
+        store_packed(qk, D >> 6, c, e, acc * qscale);
+    } else if ((idx -= n_qk) < n_iv) {      // W_iv[j][c] = sum_d W_ih[j][d] Wv[d][c]
+        const int j = idx / C, c = idx % C;
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc = fmaf(w_ih[j * D + d], wv[d * C + c], acc);
+        store_packed(iv, C >> 6, j, c, acc);
+    } else if ((idx -= n_iv) < n_hh) {
+        store_packed(hh, D >> 6, idx / D, idx % D, w_hh[idx]);
+    } else if ((idx -= n_hh) < n_1) {
+        store_packed(p1, D >> 6, idx / D, idx % D, w1[idx]);
+    } else if ((idx -= n_1) < n_2) {
+        store_packed(p2, DM >> 6, idx / DM, idx % DM, w2[idx]);
+    }
+}
+
+// ============================================================================================
+// update kernel
+// ============================================================================================
+struct URing {
+    unsigned char* stages;
+    uint64_t* full;
+    uint64_t* empty;
+    int nstage;
+};
+
+struct UProducer {
+    static constexpr bool kConsumer = false;
+    URing ring;
+    uint32_t pidx;
+    uint64_t pol;
+    template <class Acc>
+    __device__ __forceinline__ void gemm(const __half* base, int kpt, int nb, int nkb, const __half*,
+                                         const __half*, int, Acc&) {
+        for (int kb = 0; kb < nkb; ++kb, ++pidx) {
+            const int s = pidx % ring.nstage;
+            mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+            mbar_arrive_expect_tx(&ring.full[s], PAIR_BYTES);
+            bulk_g2s(ring.stages + (size_t)s * PAIR_BYTES, base + ((size_t)nb * kpt + kb) * PAIR_HALVES,
+                     PAIR_BYTES, &ring.full[s], pol);
+        }
+    }
+    __device__ __forceinline__ void sync() {}
+};
+
+template <int NMB>
+struct UConsumer {
+    static constexpr bool kConsumer = true;
+    URing ring;
+    uint32_t pidx;
+    int warp, lane;
+    __device__ __forceinline__ void sync() { named_bar_sync(1, UPD_THREADS); }
+    // acc[mb][e] += A[16*NMB x 64*nkb] * W[panel nb]^T  for this warp's 8 output columns
+    __device__ __forceinline__ void gemm(const __half*, int, int, int nkb, const __half* Ahi,
+                                         const __half* Alo, int lda, float (&acc)[NMB][4]) {
+        const uint32_t ah_u32 = smem_u32(Ahi), al_u32 = smem_u32(Alo);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb, ++pidx) {
+            const int s = pidx % ring.nstage;
+            mbar_wait(&ring.full[s], (pidx / ring.nstage) & 1);
+            const uint32_t pan = smem_u32(ring.stages + (size_t)s * PAIR_BYTES);
+            uint32_t bh[4][2], bl[4][2];
+            {
+                const int row = 8 * warp + (lane & 7);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t r4[4];
+                    const uint32_t off = row * 128 + (((4 * hf + (lane >> 3)) ^ (row & 7)) << 4);
+                    ldsm_x4(r4, pan + off);
+                    bh[2 * hf][0] = r4[0]; bh[2 * hf][1] = r4[1]; bh[2 * hf + 1][0] = r4[2]; bh[2 * hf + 1][1] = r4[3];
+                    ldsm_x4(r4, pan + 64 * 64 * 2 + off);
+                    bl[2 * hf][0] = r4[0]; bl[2 * hf][1] = r4[1]; bl[2 * hf + 1][0] = r4[2]; bl[2 * hf + 1][1] = r4[3];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[s]);
+#pragma unroll
+            for (int mb = 0; mb < NMB; ++mb) {
+                const int row = 16 * mb + (lane & 7) + ((lane >> 3) & 1) * 8;
+                uint32_t ah[4][4], al[4][4];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t off = (uint32_t)(row * lda + kb * 64 + 16 * ks + (lane >> 4) * 8) * 2u;
+                    ldsm_x4(ah[ks], ah_u32 + off);
+                    ldsm_x4(al[ks], al_u32 + off);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    mma_f16(acc[mb], ah[ks], bh[ks][0], bh[ks][1]);
+                    mma_f16(acc[mb], al[ks], bh[ks][0], bh[ks][1]);
+                    mma_f16(acc[mb], ah[ks], bl[ks][0], bl[ks][1]);
+                }
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ void store_split(__half* hi, __half* lo, int idx, float v) {
+    const __half h = __float2half_rn(v);
+    hi[idx] = h;
+    lo[idx] = __float2half_rn(v - __half2float(h));
+}
+
+// LayerNorm rows of `src` (fp32, stride lds) -> fp16 hi/lo operand buffers; one warp per row
+template <int D>
+__device__ __forceinline__ void ln_rows_split(const float* src, int lds, __half* hi, __half* lo, int lda,
+                                              int rows, const float* __restrict__ gw,
+                                              const float* __restrict__ gb, int warp, int lane) {
+    constexpr int PER = D / 32;
+    float gm[PER], bt[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { gm[i] = __ldg(gw + lane + 32 * i); bt[i] = __ldg(gb + lane + 32 * i); }
+    for (int r = warp; r < rows; r += UPD_WARPS) {
+        float v[PER];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { v[i] = src[r * lds + lane + 32 * i]; s += v[i]; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mu = s * (1.f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { v[i] -= mu; q = fmaf(v[i], v[i], q); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.f / D) + LN_EPS);
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            store_split(hi, lo, r * lda + lane + 32 * i, fmaf(v[i] * rstd, gm[i], bt[i]));
+    }
+}
+
+template <int C, int NMB>
+struct UpdCfg {
+    static constexpr int D = C, DM = 2 * C, ROWS = 16 * NMB;
+    static constexpr int LDA = C + 8, LDH = DM + 8, LDS = D + 4;
+    static constexpr int OFF_A = 0;                                  // a_hi | a_lo
+    static constexpr int OFF_H = OFF_A + 2 * ROWS * LDA * 2;         // h_hi | h_lo (also previous slots)
+    static constexpr int OFF_SP = OFF_H + 2 * ROWS * LDH * 2;        // fp32 state
+    static constexpr int OFF_BARS = OFF_SP + ROWS * LDS * 4;
+    static constexpr int OFF_RING = (OFF_BARS + 2 * 8 * 8 + 1023) / 1024 * 1024;
+    static constexpr int NST_FIT = (232448 - OFF_RING) / PAIR_BYTES;
+    static constexpr int NST = NST_FIT > 8 ? 8 : NST_FIT;
+    static_assert(NST >= 3, "update kernel: shared memory budget");
+    static constexpr int SMEM = OFF_RING + NST * PAIR_BYTES;
+};
+
+template <int C, int NMB, class Role>
+__device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, unsigned char* smem, int tid,
+                                           int warp, int lane) {
+    using Cfg = UpdCfg<C, NMB>;
+    constexpr int D = Cfg::D, DM = Cfg::DM, ROWS = Cfg::ROWS, LDA = Cfg::LDA, LDH = Cfg::LDH, LDS = Cfg::LDS;
+    __half* a_hi = reinterpret_cast<__half*>(smem + Cfg::OFF_A);
+    __half* a_lo = a_hi + ROWS * LDA;
+    __half* h_hi = reinterpret_cast<__half*>(smem + Cfg::OFF_H);
+    __half* h_lo = h_hi + ROWS * LDH;
+    float* sp = reinterpret_cast<float*>(smem + Cfg::OFF_SP);
+    const SAWeightsDev& w = p.w;
+    const int K = p.K, N = p.N;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int fl0 = (int)blockIdx.x * (ROWS / 8);            // first local frame of this CTA
+    const int fbase = p.frame0 + fl0;
+    auto row_ok = [&](int r) { return (fl0 + (r >> 3)) < p.nframes && (r & 7) < K; };
+
+    if (p.do_update) {
+        if (Role::kConsumer) {
+            // ---- u^ = (sum_chunks U / 1024 + eps*xsum) / (sum_chunks colsum / 1024 + N*eps) ----
+            for (int r = warp; r < ROWS; r += UPD_WARPS) {
+                const int f = fbase + (r >> 3), slot = r & 7;
+                const bool ok = row_ok(r);
+                float den = 1.f;
+                if (ok) {
+                    float cs = 0.f;
+                    for (int ch = 0; ch < p.nchunk; ++ch)
+                        cs += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + 8 * C + slot);
+                    den = cs * (1.f / SA_PSCALE) + (float)N * p.eps;
+                }
+#pragma unroll
+                for (int i = 0; i < C / 32; ++i) {
+                    const int c = lane + 32 * i;
+                    float u = 0.f, sprev = 0.f;
+                    if (ok) {
+                        float us = 0.f;
+                        for (int ch = 0; ch < p.nchunk; ++ch)
+                            us += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + slot * C + c);
+                        float xsv;
+                        if (p.first) {
+                            xsv = 0.f;
+                            for (int ch = 0; ch < p.nchunk; ++ch)
+                                xsv += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + 8 * C + 8 + c);
+                            if (slot == 0) p.xsum[(size_t)f * C + c] = xsv;
+                        } else {
+                            xsv = p.xsum[(size_t)f * C + c];
+                        }
+                        u = (us * (1.f / SA_PSCALE) + p.eps * xsv) / den;
+                        sprev = __ldg(p.slots_prev + ((size_t)f * K + slot) * D + c);
+                    }
+                    store_split(a_hi, a_lo, r * LDA + c, u);
+                    store_split(h_hi, h_lo, r * LDH + c, sprev);     // previous slots as GEMM operand
+                    sp[r * LDS + c] = sprev;
+                }
+            }
+            R.sync();
+        }
+        // ---- GRU, 64 gate columns at a time: r,z accumulate W_iv u^ + W_hh s; n keeps both parts ----
+        for (int jb = 0; jb < D / 64; ++jb) {
+            float ar[NMB][4], az[NMB][4], ani[NMB][4], anh[NMB][4];
+#pragma unroll
+            for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { ar[mb][e] = az[mb][e] = ani[mb][e] = anh[mb][e] = 0.f; }
+            R.gemm(w.w_iv, C / 64, jb, C / 64, a_hi, a_lo, LDA, ar);
+            R.gemm(w.w_hh, D / 64, jb, D / 64, h_hi, h_lo, LDH, ar);
+            R.gemm(w.w_iv, C / 64, D / 64 + jb, C / 64, a_hi, a_lo, LDA, az);
+            R.gemm(w.w_hh, D / 64, D / 64 + jb, D / 64, h_hi, h_lo, LDH, az);
+            R.gemm(w.w_iv, C / 64, 2 * (D / 64) + jb, C / 64, a_hi, a_lo, LDA, ani);
+            R.gemm(w.w_hh, D / 64, 2 * (D / 64) + jb, D / 64, h_hi, h_lo, LDH, anh);
+            if (Role::kConsumer) {
+                const int col0 = 64 * jb + 8 * warp + 2 * t4;
+                float bir[2], bhr[2], biz[2], bhz[2], bin_[2], bhn[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    bir[q] = __ldg(w.b_ih + col0 + q); bhr[q] = __ldg(w.b_hh + col0 + q);
+                    biz[q] = __ldg(w.b_ih + D + col0 + q); bhz[q] = __ldg(w.b_hh + D + col0 + q);
+                    bin_[q] = __ldg(w.b_ih + 2 * D + col0 + q); bhn[q] = __ldg(w.b_hh + 2 * D + col0 + q);
+                }
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int row = 16 * mb + g + 8 * (e >> 1), q = e & 1, col = col0 + q;
+                        const float r_ = sigmoidf_(ar[mb][e] + bir[q] + bhr[q]);
+                        const float z_ = sigmoidf_(az[mb][e] + biz[q] + bhz[q]);
+                        const float n_ = tanhf(ani[mb][e] + bin_[q] + r_ * (anh[mb][e] + bhn[q]));
+                        const float prev = sp[row * LDS + col];
+                        sp[row * LDS + col] = (1.f - z_) * n_ + z_ * prev;     // s'
+                    }
+            }
+        }
+        if (Role::kConsumer) {
+            R.sync();
+            ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, w.ln_m_w, w.ln_m_b, warp, lane);
+            R.sync();
+        }
+        // ---- MLP hidden: h = relu(LN(s') W1^T + b1) ----
+        for (int nb = 0; nb < DM / 64; ++nb) {
+            float acc[NMB][4];
+#pragma unroll
+            for (int mb = 0; mb < NMB; ++mb) acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f;
+            R.gemm(w.w1, D / 64, nb, D / 64, a_hi, a_lo, LDA, acc);
+            if (Role::kConsumer) {
+                const int col0 = 64 * nb + 8 * warp + 2 * t4;
+                const float b0 = __ldg(w.b1 + col0), b1v = __ldg(w.b1 + col0 + 1);
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int row = 16 * mb + g + 8 * (e >> 1);
+                        store_split(h_hi, h_lo, row * LDH + col0 + (e & 1),
+                                    fmaxf(acc[mb][e] + ((e & 1) ? b1v : b0), 0.f));
+                    }
+            }
+        }
+        if (Role::kConsumer) R.sync();
+        // ---- s_new = s' + h W2^T + b2 ----
+        for (int nb = 0; nb < D / 64; ++nb) {
+            float acc[NMB][4];
+#pragma unroll
+            for (int mb = 0; mb < NMB; ++mb) acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f;
+            R.gemm(w.w2, DM / 64, nb, DM / 64, h_hi, h_lo, LDH, acc);
+            if (Role::kConsumer) {
+                const int col0 = 64 * nb + 8 * warp + 2 * t4;
+                const float b0 = __ldg(w.b2 + col0), b1v = __ldg(w.b2 + col0 + 1);
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int row = 16 * mb + g + 8 * (e >> 1), col = col0 + (e & 1);
+                        const float sn = sp[row * LDS + col] + acc[mb][e] + ((e & 1) ? b1v : b0);
+                        sp[row * LDS + col] = sn;
+                        if (row_ok(row))
+                            p.slots_out[((size_t)(fbase + (row >> 3)) * K + (row & 7)) * D + col] = sn;
+                    }
+            }
+        }
+        if (Role::kConsumer) R.sync();
+    } else if (Role::kConsumer) {
+        for (int r = warp; r < ROWS; r += UPD_WARPS) {
+            const bool ok = row_ok(r);
+#pragma unroll
+            for (int i = 0; i < D / 32; ++i) {
+                const int c = lane + 32 * i;
+                sp[r * LDS + c] = ok ? __ldg(p.slots_prev + ((size_t)(fbase + (r >> 3)) * K + (r & 7)) * D + c) : 0.f;
+            }
+        }
+        R.sync();
+    }
+
+    if (p.do_q) {
+        // ---- q~ = LNq(S) W_qk^T -> fp16 hi/lo, rows >= K are zero ----
+        if (Role::kConsumer) {
+            ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, w.ln_q_w, w.ln_q_b, warp, lane);
+            R.sync();
+        }
+        for (int nb = 0; nb < C / 64; ++nb) {
+            float acc[NMB][4];
+#pragma unroll
+            for (int mb = 0; mb < NMB; ++mb) acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f;
+            R.gemm(w.w_qk, D / 64, nb, D / 64, a_hi, a_lo, LDA, acc);
+            if (Role::kConsumer) {
+                const int col0 = 64 * nb + 8 * warp + 2 * t4;
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int row = 16 * mb + g + 8 * (e >> 1), col = col0 + (e & 1);
+                        if (fl0 + (row >> 3) < p.nframes) {
+                            const float v = ((row & 7) < K) ? acc[mb][e] : 0.f;
+                            __half* qh = p.qt + (size_t)(fbase + (row >> 3)) * (2 * 8 * C) + (row & 7) * C + col;
+                            const __half hv = __float2half_rn(v);
+                            qh[0] = hv;
+                            qh[8 * C] = __float2half_rn(v - __half2float(hv));
+                        }
+                    }
+            }
+        }
+    }
+}
+
+template <int C, int NMB>
+__global__ void __launch_bounds__(UPD_THREADS + 32, 1) sa_update_kernel(const SAUpdateParams p) {
+    using Cfg = UpdCfg<C, NMB>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+    URing ring{smem + Cfg::OFF_RING, bars, bars + 8, Cfg::NST};
+    if (tid == 0) {
+        for (int s = 0; s < Cfg::NST; ++s) { mbar_init(&ring.full[s], 1); mbar_init(&ring.empty[s], UPD_WARPS); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == UPD_WARPS) {
+        if (lane == 0) {
+            UProducer P{ring, 0u, l2_policy_evict_last()};
+            run_update<C, NMB>(P, p, smem, tid, warp, lane);
+        }
+        return;
+    }
+    UConsumer<NMB> Cn{ring, 0u, warp, lane};
+    run_update<C, NMB>(Cn, p, smem, tid, warp, lane);
+}
+
+// ============================================================================================
+// host side
+// ============================================================================================
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, int n_iter, SAWorkspace* ws) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    ws->w_qk = take((size_t)C * D * 2 * 2);
+    ws->w_iv = take((size_t)3 * D * C * 2 * 2);
+    ws->w_hh = take((size_t)3 * D * D * 2 * 2);
+    ws->w1 = take((size_t)DM * D * 2 * 2);
+    ws->w2 = take((size_t)D * DM * 2 * 2);
+    // pixel chunking: 1024-pixel items (8 warps x 8 tiles), smaller for small N
+    int chunk_px = 1024;
+    while (chunk_px > 128 && chunk_px / 2 >= N) chunk_px /= 2;
+    ws->chunk_px = chunk_px;
+    ws->nchunk = (N + chunk_px - 1) / chunk_px;
+    ws->n16 = ws->nchunk * chunk_px;
+    ws->pstride = 9 * C + 8;
+    ws->qt = take((size_t)B * 2 * 8 * C * 2);
+    ws->partials = take((size_t)B * ws->nchunk * ws->pstride * 4);
+    ws->xsum = take((size_t)B * C * 4);
+    ws->xhat_frames = (n_iter > 1) ? (chunk_frames < B ? chunk_frames : B) : 0;
+    ws->xhat = take((size_t)ws->xhat_frames * ws->n16 * C * 2);
+    ws->total = off;
+}
+
+cudaError_t sa_prep_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,
+                           const float* w_hh, const float* w1, const float* w2, char* base,
+                           const SAWorkspace& ws, int C, int D, int DM, cudaStream_t st) {
+    const int total = C * D + 3 * D * C + 3 * D * D + DM * D + D * DM;
+    const float qscale = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
+    auto H = [&](size_t off) { return reinterpret_cast<__half*>(base + off); };
+    sa_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(wq, wk, wv, w_ih, w_hh, w1, w2, H(ws.w_qk), H(ws.w_iv),
+                                                       H(ws.w_hh), H(ws.w1), H(ws.w2), C, D, DM, qscale);
+    return cudaGetLastError();
+}
+
+template <int C, int NMB>
+static cudaError_t update_launch_t(const SAUpdateParams& p, cudaStream_t st) {
+    using Cfg = UpdCfg<C, NMB>;
+    auto kern = sa_update_kernel<C, NMB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    const int frames_per_cta = Cfg::ROWS / 8;
+    const int grid = (p.nframes + frames_per_cta - 1) / frames_per_cta;
+    kern<<<grid, UPD_THREADS + 32, Cfg::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st) {
+    // 16*NMB rows per CTA: the most rows (fewest weight re-reads) that still gives every SM a CTA
+    const bool big = p.nframes >= 4 * sms;
+    if (C == 128) return big ? update_launch_t<128, 4>(p, st) : update_launch_t<128, 2>(p, st);
+    return update_launch_t<192, 2>(p, st);
+}
+
+}  // namespace sfb

@@ -69,10 +69,8 @@ def load():
     lib.sfb_launch_count.restype = c.c_longlong
     lib.sfb_debug_set_profile.restype = None
     lib.sfb_debug_set_profile.argtypes = [c.c_void_p, c.c_int]
-    lib.sfb_debug_sa_max_clusters.restype = c.c_int
-    lib.sfb_debug_sa_max_clusters.argtypes = [c.c_int, c.c_int]
     lib.sfb_sa_workspace_bytes.restype = c.c_size_t
-    lib.sfb_sa_workspace_bytes.argtypes = [c.c_int, c.c_int]
+    lib.sfb_sa_workspace_bytes.argtypes = [c.c_int] * 7
     lib.sfb_sa_forward.restype = c.c_int
     lib.sfb_sa_forward.argtypes = [
         c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p,
@@ -95,7 +93,7 @@ def load():
 def exported_symbols():
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
     return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_debug_set_profile',
-            'sfb_debug_sa_max_clusters', 'sfb_sa_workspace_bytes',
+            'sfb_sa_workspace_bytes',
             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
             'sfb_rollout_forward']
 
@@ -134,7 +132,7 @@ class SlotAttentionEngine:
         self._ws = None
 
     def forward(self, feats, slots, weights, num_iterations, eps, mlp_hidden_size,
-                return_mask=False, cluster_size=0):
+                return_mask=False, chunk_frames=0):
         """feats [B,N,C] f32 (rows contiguous; batch stride free), slots [B,K,D] f32.
 
         ``weights``: dict state_dict-key -> CUDA f32 tensor (SA_WEIGHT_KEYS).
@@ -155,7 +153,10 @@ class SlotAttentionEngine:
         if B == 0:
             out = feats.new_zeros((0, K, D))
             return (out, feats.new_zeros((0, K, N))) if return_mask else out
-        ws_bytes = int(lib.sfb_sa_workspace_bytes(C, D))
+        ws_bytes = int(lib.sfb_sa_workspace_bytes(B, N, C, D, int(mlp_hidden_size),
+                                                  int(num_iterations), int(chunk_frames)))
+        if ws_bytes == 0:
+            raise SfbError(f'unsupported Slot Attention shape B={B} N={N} C={C} D={D}')
         if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         wt = []
@@ -172,7 +173,7 @@ class SlotAttentionEngine:
             rc = lib.sfb_sa_forward(
                 feats.data_ptr(), SFB_DTYPE_F32, bstride, slots.data_ptr(), out.data_ptr(),
                 mask.data_ptr() if return_mask else None, ctypes.byref(cw), B, N, C, D,
-                int(mlp_hidden_size), K, int(num_iterations), float(eps), int(cluster_size),
+                int(mlp_hidden_size), K, int(num_iterations), float(eps), int(chunk_frames),
                 self._ws.data_ptr(), ws_bytes, _stream(dev))
         _check(rc)
         if return_mask:

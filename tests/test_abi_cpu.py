@@ -37,10 +37,13 @@ def test_version_and_strerror(lib):
 
 
 def test_workspace_sizes(lib):
-    # folded projections: W_qk [C,D] + W_iv [3D,C], fp32
-    assert lib.sfb_sa_workspace_bytes(128, 128) == (128 * 128 + 3 * 128 * 128) * 4
-    assert lib.sfb_sa_workspace_bytes(192, 192) == (192 * 192 * 4) * 4
-    assert lib.sfb_sa_workspace_bytes(0, 128) == 0
+    # grows with the batch (q~, partials) and with the x^ ring of one frame chunk
+    a = lib.sfb_sa_workspace_bytes(8, 4096, 128, 128, 256, 2, 0)
+    b = lib.sfb_sa_workspace_bytes(16, 4096, 128, 128, 256, 2, 0)
+    one_iter = lib.sfb_sa_workspace_bytes(8, 4096, 128, 128, 256, 1, 0)
+    assert 0 < one_iter < a < b
+    assert a - one_iter >= 8 * 4096 * 128 * 2          # fp16 x^ ring only when n_iter > 1
+    assert lib.sfb_sa_workspace_bytes(0, 4096, 128, 128, 256, 2, 0) == 0
     # fp16 copies of in/out proj + per-layer qkv, out, ffn1, ffn2
     d, Ds, F, L = 128, 128, 512, 4
     want = (2 * d * Ds + L * (3 * d * d + d * d + 2 * F * d)) * 2

@@ -45,7 +45,7 @@ def test_slot_attention_vs_oracle(name):
     assert rel_max(out.cpu().numpy(), ref) < 1e-3
 
 
-def test_slot_attention_cluster16_and_strided_input():
+def test_slot_attention_chunked_and_strided_input():
     c, w, feats, slots = cases.sa_case('sa_cfg2')
     g = golden('sa_cfg2')
     m = sa_module(c, w, DEV)
@@ -54,8 +54,13 @@ def test_slot_attention_cluster16_and_strided_input():
     big[:, 1] = torch.from_numpy(feats).to(DEV)
     with torch.no_grad():
         out_strided = m(big[:, 1], torch.from_numpy(slots).to(DEV))
-        m.cluster_size = 16
+        m.chunk_frames = 3           # 8 frames in chunks of 3, 3, 2 (x^ ring reuse)
         out16 = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
+        m.chunk_frames = 0
+        out_all = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
+    assert torch.equal(out16, out_all)
+    with torch.no_grad():
+        pass
     assert rel_max(out_strided.cpu().numpy(), g['slots_f64']) < 1e-3
     assert rel_max(out16.cpu().numpy(), g['slots_f64']) < 1e-3
 
