@@ -57,6 +57,10 @@ long long sfb_launch_count(void);
  * %globaltimer stamps at phase boundaries (cluster 0 / CTA 0); pass NULL to switch it off.
  */
 void sfb_debug_set_profile(void* device_buf, int capacity);
+/* self-test of the tcgen05 path: out[N][M] = X[N][K] W[M][K]^T (fp16 operands, fp32 accumulate);
+ * M % 128 == 0, 16 <= N <= 128 (N % 16 == 0), K % 64 == 0; workspace >= M*K*2 bytes. */
+int sfb_debug_umma_gemm(const float* W, const float* X, float* out, int M, int N, int K, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Hot path 1: Slot Attention                                                 */

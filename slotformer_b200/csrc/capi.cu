@@ -73,6 +73,18 @@ const char* sfb_strerror(int code) {
     return "unknown error";
 }
 
+int sfb_debug_umma_gemm(const float* W, const float* X, float* out, int M, int N, int K, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!W || !X || !out || !workspace) return SFB_E_NULL;
+    if (M < 128 || M % 128 || N < 16 || N > 128 || N % 16 || K < 64 || K % 64) return SFB_E_BAD_SHAPE;
+    if (workspace_bytes < (size_t)M * K * 2) return SFB_E_WORKSPACE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = sfb::ro_pack2_launch(W, reinterpret_cast<__half*>(workspace), M, K, st);
+    if (e != cudaSuccess) return cuda_err(e);
+    e = sfb::umma_test_launch(reinterpret_cast<const __half*>(workspace), X, out, M, N, K, st);
+    return cuda_err(e);
+}
+
 // ------------------------------------------------------------------------------------------
 // Slot Attention
 // ------------------------------------------------------------------------------------------
@@ -123,7 +135,8 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
 
     cudaError_t e = sfb::sa_prep_launch(w->project_q_1_weight, w->project_k_weight, w->project_v_weight,
                                         w->gru_weight_ih, w->gru_weight_hh, w->mlp_1_weight,
-                                        w->mlp_3_weight, base, ws, C, D, Dm, st);
+                                        w->mlp_3_weight, w->norm_inputs_weight, w->norm_inputs_bias, base, ws,
+                                        C, D, Dm, st);
     if (e != cudaSuccess) return cuda_err(e);
     g_launches.fetch_add(1);
 
@@ -133,6 +146,9 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     up.w.b_ih = w->gru_bias_ih; up.w.b_hh = w->gru_bias_hh; up.w.b1 = w->mlp_1_bias; up.w.b2 = w->mlp_3_bias;
     up.w.ln_q_w = w->project_q_0_weight; up.w.ln_q_b = w->project_q_0_bias;
     up.w.ln_m_w = w->mlp_0_weight; up.w.ln_m_b = w->mlp_0_bias;
+    up.w.ln_in_w = w->norm_inputs_weight; up.w.ln_in_b = w->norm_inputs_bias;
+    up.w.wbeta = reinterpret_cast<const float*>(base + ws.wbeta);
+    up.qt_stride = ws.qt_stride;
     up.partials = reinterpret_cast<const float*>(base + ws.partials);
     up.xsum = reinterpret_cast<float*>(base + ws.xsum);
     up.slots_out = slots_out;

@@ -9,37 +9,51 @@ static constexpr int RO_THREADS = RO_WARPS * 32;
 static constexpr float RO_LN_EPS = 1e-5f;
 
 // LayerNorm rows [0, L) of h (fp32, stride d) -> fp16 rows of `out` (stride ldo); rows [L, Lp) = 0
-template <int DMODEL>
+template <int DMODEL, int RPW>
 __device__ __forceinline__ void ln_to_half(const float* h, __half* out, int ldo, int L, int Lp,
-                                           const float* __restrict__ gw, const float* __restrict__ gb,
-                                           int warp, int lane) {
+                                           const float* gw, const float* gb, int warp, int lane) {
+    constexpr int PER0 = DMODEL / 32;
+    float gmm[PER0], bta[PER0];
+#pragma unroll
+    for (int i = 0; i < PER0; ++i) { gmm[i] = gw[lane + 32 * i]; bta[i] = gb[lane + 32 * i]; }
+  for (int row0 = 0; row0 < Lp; row0 += RO_WARPS * RPW) {
+    // warp w normalises rows w, w+8, ...; RPW = max rows per warp.  All rows are loaded first and
+    // their reductions are interleaved, so the shuffle latency is paid once, not once per row.
     constexpr int PER = DMODEL / 32;
-    float gmm[PER], bta[PER];
+    float v[RPW][PER], s[RPW], q[RPW];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { gmm[i] = gw[lane + 32 * i]; bta[i] = gb[lane + 32 * i]; }
-    for (int r = warp; r < Lp; r += RO_WARPS) {
-        if (r < L) {
-            float v[PER];
-            float s = 0.f;
+    for (int j = 0; j < RPW; ++j) {
+        const int r = row0 + warp + RO_WARPS * j;
+        s[j] = 0.f;
 #pragma unroll
-            for (int i = 0; i < PER; ++i) { v[i] = h[r * DMODEL + lane + 32 * i]; s += v[i]; }
+        for (int i = 0; i < PER; ++i) { v[j][i] = (r < L) ? h[r * DMODEL + lane + 32 * i] : 0.f; s[j] += v[j][i]; }
+    }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mu = s * (1.f / DMODEL);
-            float q = 0.f;
+    for (int o = 16; o; o >>= 1)
 #pragma unroll
-            for (int i = 0; i < PER; ++i) { v[i] -= mu; q = fmaf(v[i], v[i], q); }
+        for (int j = 0; j < RPW; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const float rstd = rsqrtf(q * (1.f / DMODEL) + RO_LN_EPS);
+    for (int j = 0; j < RPW; ++j) {
+        const float mu = s[j] * (1.f / DMODEL);
+        q[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { v[j][i] -= mu; q[j] = fmaf(v[j][i], v[j][i], q[j]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int r = row0 + warp + RO_WARPS * j;
+        if (r < Lp) {
+            const float rstd = rsqrtf(q[j] * (1.f / DMODEL) + RO_LN_EPS);
 #pragma unroll
             for (int i = 0; i < PER; ++i)
-                out[r * ldo + lane + 32 * i] = __float2half_rn(fmaf(v[i] * rstd, gmm[i], bta[i]));
-        } else {
-#pragma unroll
-            for (int i = 0; i < PER; ++i) out[r * ldo + lane + 32 * i] = __float2half_rn(0.f);
+                out[r * ldo + lane + 32 * i] = __float2half_rn(r < L ? fmaf(v[j][i] * rstd, gmm[i], bta[i]) : 0.f);
         }
     }
+  }
 }
 
 // One (head, 16-query block) of softmax(Q K^T / sqrt(dh)) V.  Q/K/V live in `buf` (fp16, stride
@@ -130,6 +144,130 @@ __device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qco
         const int col = qcol + 8 * nb + 2 * t4;
         *reinterpret_cast<__half2*>(buf + (16 * mb + g) * ldb + col) = __floats2half2_rn(o[nb][0] * i0, o[nb][1] * i0);
         *reinterpret_cast<__half2*>(buf + (16 * mb + g + 8) * ldb + col) = __floats2half2_rn(o[nb][2] * i1, o[nb][3] * i1);
+    }
+}
+
+// All (<= NMB) 16-query blocks of one head in one go: K/V fragments are loaded once and the
+// independent per-block chains (MMA -> shuffles -> exp2 -> MMA) interleave.  Used when the window
+// is short (NMB * NKB accumulators fit in registers).
+template <int DH, int NKB, int NMB>
+__device__ __forceinline__ void attn_head(__half* buf, int ldb, int nmb, int qcol, int kcol, int vcol,
+                                          int L, int nkb, float sm_scale_log2, int lane) {
+    const int g = lane >> 2, t4 = lane & 3;
+    const uint32_t b_u32 = smem_u32(buf);
+    uint32_t qf[NMB][DH / 16][4];
+#pragma unroll
+    for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+            const int row = 16 * (mb < nmb ? mb : 0) + (lane & 7) + ((lane >> 3) & 1) * 8;
+            ldsm_x4(qf[mb][ks], b_u32 + (uint32_t)(row * ldb + qcol + 16 * ks + (lane >> 4) * 8) * 2u);
+        }
+    float s[NMB][NKB][4];
+#pragma unroll
+    for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NKB; ++nb) { s[mb][nb][0] = s[mb][nb][1] = s[mb][nb][2] = s[mb][nb][3] = 0.f; }
+#pragma unroll
+    for (int nb = 0; nb < NKB; nb += 2) {
+        if (nb < nkb) {
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks) {
+                uint32_t kf[4];
+                const int row = 8 * nb + (lane & 7) + (lane >> 4) * 8;
+                ldsm_x4(kf, b_u32 + (uint32_t)(row * ldb + kcol + 16 * ks + ((lane >> 3) & 1) * 8) * 2u);
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb) {
+                    mma_f16(s[mb][nb], qf[mb][ks], kf[0], kf[1]);
+                    mma_f16(s[mb][nb + 1], qf[mb][ks], kf[2], kf[3]);
+                }
+            }
+        }
+    }
+    float m0[NMB], m1[NMB], l0[NMB], l1[NMB];
+#pragma unroll
+    for (int mb = 0; mb < NMB; ++mb) {
+        m0[mb] = -INFINITY; m1[mb] = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < NKB; ++nb) {
+            if (nb < nkb) {
+                const int c = 8 * nb + 2 * t4;
+                s[mb][nb][0] = (c < L) ? s[mb][nb][0] * sm_scale_log2 : -INFINITY;
+                s[mb][nb][1] = (c + 1 < L) ? s[mb][nb][1] * sm_scale_log2 : -INFINITY;
+                s[mb][nb][2] = (c < L) ? s[mb][nb][2] * sm_scale_log2 : -INFINITY;
+                s[mb][nb][3] = (c + 1 < L) ? s[mb][nb][3] * sm_scale_log2 : -INFINITY;
+                m0[mb] = fmaxf(m0[mb], fmaxf(s[mb][nb][0], s[mb][nb][1]));
+                m1[mb] = fmaxf(m1[mb], fmaxf(s[mb][nb][2], s[mb][nb][3]));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+        for (int mb = 0; mb < NMB; ++mb) {
+            m0[mb] = fmaxf(m0[mb], __shfl_xor_sync(0xffffffffu, m0[mb], o));
+            m1[mb] = fmaxf(m1[mb], __shfl_xor_sync(0xffffffffu, m1[mb], o));
+        }
+    uint32_t pf[NMB][NKB][2];
+#pragma unroll
+    for (int mb = 0; mb < NMB; ++mb) {
+        l0[mb] = 0.f; l1[mb] = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < NKB; ++nb) {
+            if (nb < nkb) {
+                const float e0 = exp2f(s[mb][nb][0] - m0[mb]), e1 = exp2f(s[mb][nb][1] - m0[mb]);
+                const float e2 = exp2f(s[mb][nb][2] - m1[mb]), e3 = exp2f(s[mb][nb][3] - m1[mb]);
+                const __half2 h01 = __floats2half2_rn(e0, e1), h23 = __floats2half2_rn(e2, e3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                l0[mb] += f01.x + f01.y; l1[mb] += f23.x + f23.y;
+                pf[mb][nb][0] = *reinterpret_cast<const uint32_t*>(&h01);
+                pf[mb][nb][1] = *reinterpret_cast<const uint32_t*>(&h23);
+            } else {
+                pf[mb][nb][0] = pf[mb][nb][1] = 0u;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+        for (int mb = 0; mb < NMB; ++mb) {
+            l0[mb] += __shfl_xor_sync(0xffffffffu, l0[mb], o);
+            l1[mb] += __shfl_xor_sync(0xffffffffu, l1[mb], o);
+        }
+    float o_[NMB][DH / 8][4];
+#pragma unroll
+    for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < DH / 8; ++nb) { o_[mb][nb][0] = o_[mb][nb][1] = o_[mb][nb][2] = o_[mb][nb][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < NKB / 2; ++kk) {
+        if (2 * kk < nkb) {
+#pragma unroll
+            for (int nb = 0; nb < DH / 8; nb += 2) {
+                uint32_t vf[4];
+                const int row = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+                ldsm_x4_t(vf, b_u32 + (uint32_t)(row * ldb + vcol + 8 * nb + (lane >> 4) * 8) * 2u);
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb) {
+                    const uint32_t a[4] = {pf[mb][2 * kk][0], pf[mb][2 * kk][1], pf[mb][2 * kk + 1][0], pf[mb][2 * kk + 1][1]};
+                    mma_f16(o_[mb][nb], a, vf[0], vf[1]);
+                    mma_f16(o_[mb][nb + 1], a, vf[2], vf[3]);
+                }
+            }
+        }
+    }
+    __syncwarp();   // every lane holds its Q fragments; the Q blocks may now be overwritten
+#pragma unroll
+    for (int mb = 0; mb < NMB; ++mb) {
+        if (mb < nmb) {
+            const float i0 = 1.f / l0[mb], i1 = 1.f / l1[mb];
+#pragma unroll
+            for (int nb = 0; nb < DH / 8; ++nb) {
+                const int col = qcol + 8 * nb + 2 * t4;
+                *reinterpret_cast<__half2*>(buf + (16 * mb + g) * ldb + col) = __floats2half2_rn(o_[mb][nb][0] * i0, o_[mb][nb][1] * i0);
+                *reinterpret_cast<__half2*>(buf + (16 * mb + g + 8) * ldb + col) = __floats2half2_rn(o_[mb][nb][2] * i1, o_[mb][nb][3] * i1);
+            }
+        }
     }
 }
 

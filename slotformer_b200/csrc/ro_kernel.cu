@@ -171,13 +171,29 @@ struct Consumer {
 // ----------------------------------------------------------------------------
 template <int DMODEL, int DH, int NKB, class Role>
 __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h, __half* abuf, __half* bbuf,
-                                            const float* lnp, int tid, int warp, int lane) {
+                                            float* par, int tid, int warp, int lane) {
     const int K = p.K, Ds = p.Ds, F = p.F;
     const int lda = p.lda, ldb = p.ldb;
     const int HG = p.hg, FC = p.fc;
     const int hgw = HG * DH;
     const float sm_scale_log2 = rsqrtf((float)DH) * 1.4426950408889634f;
     auto no_pre = [](int) { return make_float2(0.f, 0.f); };
+    const int PF = p.par_floats;
+    // per-layer parameter block in smem: bqkv[3d] bo[d] b1[F] b2[d] ln1w ln1b ln2w ln2b [d each]
+    auto load_params = [&](int layer, int buf) {
+        const ROLayer& ly = p.layer[layer];
+        float* dst = par + (size_t)buf * PF;
+        const float* srcs[8] = {ly.bqkv, ly.bo, ly.b1, ly.b2, ly.ln1w, ly.ln1b, ly.ln2w, ly.ln2b};
+        const int lens[8] = {3 * DMODEL, DMODEL, F, DMODEL, DMODEL, DMODEL, DMODEL, DMODEL};
+        int off = 0;
+        for (int sgm = 0; sgm < 8; ++sgm) {
+            for (int i = tid * 4; i < lens[sgm]; i += RO_THREADS * 4) cp_async16(dst + off + i, srcs[sgm] + i);
+            off += lens[sgm];
+        }
+        cp_async_commit();
+    };
+    uint32_t lcount = 0;   // layers executed so far -> parameter buffer parity
+    if (Role::kConsumer) { load_params(0, 0); cp_async_wait_all(); R.sync(); }
     int pidx_prof = 0;
     const bool do_prof = Role::kConsumer && (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
     auto stamp = [&]() { if (do_prof && pidx_prof < p.prof_cap) p.prof[pidx_prof++] = globaltimer_ns(); };
@@ -229,12 +245,21 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
 
             for (int layer = 0; layer < p.layers; ++layer) {
                 const ROLayer& ly = p.layer[layer];
-                const float* l1w = lnp ? lnp + (size_t)layer * 4 * DMODEL : ly.ln1w;
-                const float* l1b = lnp ? l1w + DMODEL : ly.ln1b;
-                const float* l2w = lnp ? l1w + 2 * DMODEL : ly.ln2w;
-                const float* l2b = lnp ? l1w + 3 * DMODEL : ly.ln2b;
+                const float* pb = par + (size_t)(p.par_double ? (lcount & 1) : 0) * PF;
+                if (Role::kConsumer && !p.par_double && lcount > 0) {   // single buffer: load now
+                    load_params(layer, 0); cp_async_wait_all(); R.sync();
+                }
+                const float* s_bqkv = pb;
+                const float* s_bo = pb + 3 * DMODEL;
+                const float* s_b1 = pb + 4 * DMODEL;
+                const float* s_b2 = pb + 4 * DMODEL + F;
+                const float* l1w = pb + 5 * DMODEL + F;
+                const float* l1b = l1w + DMODEL;
+                const float* l2w = l1w + 2 * DMODEL;
+                const float* l2b = l1w + 3 * DMODEL;
+                if (Role::kConsumer && p.par_double) load_params((layer + 1) % p.layers, (lcount + 1) & 1);   // prefetch next layer
                 if (Role::kConsumer) {
-                    ln_to_half<DMODEL>(h, abuf, lda, L, Lp, l1w, l1b, warp, lane);
+                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, abuf, lda, L, Lp, l1w, l1b, warp, lane);
                     R.sync();
                 }
                 stamp();   // LN1 done
@@ -243,7 +268,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                     if (HG == p.heads) {
                         const GemmOp op{ly.wqkv, DMODEL >> 6, 0, (3 * DMODEL) >> 6, 0, DMODEL >> 6};
                         R.gemm(op, abuf, lda, nmb,
-                               [&](int col) { return __ldg(reinterpret_cast<const float2*>(ly.bqkv + col)); },
+                               [&](int col) { return *reinterpret_cast<const float2*>(s_bqkv + col); },
                                [&](int row, int col, float v0, float v1, float2 bi) {
                                    *reinterpret_cast<__half2*>(bbuf + row * ldb + col) = __floats2half2_rn(v0 + bi.x, v1 + bi.y);
                                });
@@ -252,7 +277,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                             const int wrow = part * DMODEL + h0 * DH;
                             const GemmOp op{ly.wqkv, DMODEL >> 6, wrow >> 6, hgw >> 6, 0, DMODEL >> 6};
                             R.gemm(op, abuf, lda, nmb,
-                                   [&](int col) { return __ldg(reinterpret_cast<const float2*>(ly.bqkv + wrow + col)); },
+                                   [&](int col) { return *reinterpret_cast<const float2*>(s_bqkv + wrow + col); },
                                    [&](int row, int col, float v0, float v1, float2 bi) {
                                        *reinterpret_cast<__half2*>(bbuf + row * ldb + part * hgw + col) =
                                            __floats2half2_rn(v0 + bi.x, v1 + bi.y);
@@ -262,10 +287,16 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                     if (Role::kConsumer) {
                         R.sync();
                         stamp();   // qkv done
-                        for (int item = warp; item < HG * nmb; item += RO_WARPS) {
-                            const int hh = item / nmb, mb = item % nmb;
-                            attn_block<DH, NKB>(bbuf, ldb, mb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb,
-                                                sm_scale_log2, lane);
+                        if (NKB <= 6) {
+                            for (int hh = warp; hh < HG; hh += RO_WARPS)
+                                attn_head<DH, (NKB <= 6 ? NKB : 2), (NKB <= 6 ? NKB / 2 : 1)>(
+                                    bbuf, ldb, nmb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb, sm_scale_log2, lane);
+                        } else {
+                            for (int item = warp; item < HG * nmb; item += RO_WARPS) {
+                                const int hh = item / nmb, mb = item % nmb;
+                                attn_block<DH, NKB>(bbuf, ldb, mb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb,
+                                                    sm_scale_log2, lane);
+                            }
                         }
                         R.sync();
                         stamp();   // attention done
@@ -274,7 +305,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                     const bool first = (h0 == 0);
                     const GemmOp op{ly.wo, DMODEL >> 6, 0, DMODEL >> 6, (h0 * DH) >> 6, hgw >> 6};
                     R.gemm(op, bbuf, ldb, nmb,
-                           [&](int col) { return first ? __ldg(reinterpret_cast<const float2*>(ly.bo + col)) : make_float2(0.f, 0.f); },
+                           [&](int col) { return first ? *reinterpret_cast<const float2*>(s_bo + col) : make_float2(0.f, 0.f); },
                            [&](int row, int col, float v0, float v1, float2 bi) {
                                float2* hp = reinterpret_cast<float2*>(h + row * DMODEL + col);
                                float2 cur = *hp;
@@ -286,7 +317,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                 }
                 // ---- y = LN2(h);  h += W2 relu(W1 y + b1) + b2, FC hidden columns at a time ----
                 if (Role::kConsumer) {
-                    ln_to_half<DMODEL>(h, abuf, lda, L, Lp, l2w, l2b, warp, lane);
+                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, abuf, lda, L, Lp, l2w, l2b, warp, lane);
                     R.sync();
                 }
                 stamp();   // LN2 done
@@ -295,7 +326,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                     {
                         const GemmOp op{ly.w1, DMODEL >> 6, f0 >> 6, fcw >> 6, 0, DMODEL >> 6};
                         R.gemm(op, abuf, lda, nmb,
-                               [&](int col) { return __ldg(reinterpret_cast<const float2*>(ly.b1 + f0 + col)); },
+                               [&](int col) { return *reinterpret_cast<const float2*>(s_b1 + f0 + col); },
                                [&](int row, int col, float v0, float v1, float2 bi) {
                                    *reinterpret_cast<__half2*>(bbuf + row * ldb + col) =
                                        __floats2half2_rn(fmaxf(v0 + bi.x, 0.f), fmaxf(v1 + bi.y, 0.f));
@@ -307,7 +338,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                     {
                         const GemmOp op{ly.w2, F >> 6, 0, DMODEL >> 6, f0 >> 6, fcw >> 6};
                         R.gemm(op, bbuf, ldb, nmb,
-                               [&](int col) { return first ? __ldg(reinterpret_cast<const float2*>(ly.b2 + col)) : make_float2(0.f, 0.f); },
+                               [&](int col) { return first ? *reinterpret_cast<const float2*>(s_b2 + col) : make_float2(0.f, 0.f); },
                                [&](int row, int col, float v0, float v1, float2 bi) {
                                    float2* hp = reinterpret_cast<float2*>(h + row * DMODEL + col);
                                    float2 cur = *hp;
@@ -315,9 +346,11 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                                    *hp = cur;
                                });
                     }
+                    if (Role::kConsumer && p.par_double && f0 + FC >= F) cp_async_wait_all();   // next layer's parameters landed
                     R.sync();
                     stamp();   // ffn2 chunk done
                 }
+                ++lcount;
             }
 
             // ---- out_proj on the last K tokens -> pred_out[b, step] (slotformer.py:121) ----
@@ -350,7 +383,7 @@ __global__ void __launch_bounds__(RO_THREADS + 32, 1) ro_forward_kernel(const RO
     float* h = reinterpret_cast<float*>(smem + p.off_h);        // [Lmax_p][DMODEL]
     __half* abuf = reinterpret_cast<__half*>(smem + p.off_a);   // [Lmax_p][lda]
     __half* bbuf = reinterpret_cast<__half*>(smem + p.off_b);   // [Lmax_p][ldb]
-    float* lnp = p.ln_smem ? reinterpret_cast<float*>(smem + p.off_ln) : nullptr;
+    float* par = reinterpret_cast<float*>(smem + p.off_par);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
     Ring ring{smem + p.off_ring, bars, bars + 8, p.nstage};
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -359,25 +392,17 @@ __global__ void __launch_bounds__(RO_THREADS + 32, 1) ro_forward_kernel(const RO
         for (int s = 0; s < p.nstage; ++s) { mbar_init(&ring.full[s], 1); mbar_init(&ring.empty[s], 4); }
         fence_mbar_init();
     }
-    if (lnp) {
-        for (int i = tid; i < p.layers * 4 * DMODEL; i += RO_THREADS + 32) {
-            const int l = i / (4 * DMODEL), r = i % (4 * DMODEL), which = r / DMODEL, c = r % DMODEL;
-            const ROLayer& ly = p.layer[l];
-            const float* src = which == 0 ? ly.ln1w : which == 1 ? ly.ln1b : which == 2 ? ly.ln2w : ly.ln2b;
-            lnp[i] = src[c];
-        }
-    }
     __syncthreads();
 
     if (warp == RO_WARPS) {
         if (lane == 0) {
             Producer P{ring, 0u, l2_policy_evict_last()};
-            run_rollout<DMODEL, DH, NKB>(P, p, h, abuf, bbuf, lnp, tid, warp, lane);
+            run_rollout<DMODEL, DH, NKB>(P, p, h, abuf, bbuf, par, tid, warp, lane);
         }
         return;
     }
     Consumer<NKB / 2> C{ring, 0u, warp, lane};
-    run_rollout<DMODEL, DH, NKB>(C, p, h, abuf, bbuf, lnp, tid, warp, lane);
+    run_rollout<DMODEL, DH, NKB>(C, p, h, abuf, bbuf, par, tid, warp, lane);
 }
 
 // ----------------------------------------------------------------------------
@@ -396,32 +421,30 @@ int ro_plan(ROParams* p, int smem_limit, size_t* smem_bytes) {
     p->lda = wa + 8;
     const size_t h_bytes = (size_t)Lp * d * 4;
     const size_t a_bytes = (size_t)Lp * p->lda * 2;
-    const size_t ln_bytes = (size_t)p->layers * 4 * d * 4;
+    p->par_floats = 9 * d + F;
     const size_t bar_bytes = 16 * 8;
-    for (int hg = p->heads; hg >= 1; hg >>= 1) {
-        if (p->heads % hg) continue;
-        const int hgw = hg * dh;
-        if (hgw % 64) break;
-        int fc = 3 * hgw;
-        if (fc > F) fc = F;
-        fc = fc / 64 * 64;
-        const int ldb = 3 * hgw + 8;
-        const size_t b_bytes = (size_t)Lp * ldb * 2;
-        size_t fixed = h_bytes + a_bytes + b_bytes + bar_bytes;
-        fixed = (fixed + 1023) / 1024 * 1024;
-        // prefer LN parameters in smem and a deep ring; degrade gracefully for big shapes
-        for (int ln_smem = 1; ln_smem >= 0; --ln_smem) {
-            size_t avail = (size_t)smem_limit - (ln_smem ? ln_bytes : 0);
-            if (avail < fixed + 3 * (size_t)RO_PANEL_BYTES) continue;
-            int nstage = (int)((avail - fixed) / RO_PANEL_BYTES);
+    for (int par_double = 1; par_double >= 0; --par_double) {
+        const size_t par_bytes = (size_t)(par_double ? 2 : 1) * p->par_floats * 4;
+        for (int hg = p->heads; hg >= 1; hg >>= 1) {
+            if (p->heads % hg) continue;
+            const int hgw = hg * dh;
+            if (hgw % 64) break;
+            int fc = 3 * hgw;
+            if (fc > F) fc = F;
+            fc = fc / 64 * 64;
+            const int ldb = 3 * hgw + 8;
+            const size_t b_bytes = (size_t)Lp * ldb * 2;
+            size_t fixed = h_bytes + a_bytes + b_bytes + bar_bytes + par_bytes;
+            fixed = (fixed + 1023) / 1024 * 1024;
+            if ((size_t)smem_limit < fixed + 3 * (size_t)RO_PANEL_BYTES) continue;
+            int nstage = (int)(((size_t)smem_limit - fixed) / RO_PANEL_BYTES);
             if (nstage > 8) nstage = 8;
-            if (nstage < 3) continue;
-            p->hg = hg; p->fc = fc; p->ldb = ldb; p->ln_smem = ln_smem; p->nstage = nstage;
+            p->hg = hg; p->fc = fc; p->ldb = ldb; p->nstage = nstage; p->par_double = par_double;
             p->off_h = 0; p->off_a = (uint32_t)h_bytes; p->off_b = (uint32_t)(h_bytes + a_bytes);
             p->off_bars = (uint32_t)(h_bytes + a_bytes + b_bytes);
+            p->off_par = (uint32_t)(h_bytes + a_bytes + b_bytes + bar_bytes);
             p->off_ring = (uint32_t)fixed;
-            p->off_ln = (uint32_t)(fixed + (size_t)nstage * RO_PANEL_BYTES);
-            *smem_bytes = fixed + (size_t)nstage * RO_PANEL_BYTES + (ln_smem ? ln_bytes : 0);
+            *smem_bytes = fixed + (size_t)nstage * RO_PANEL_BYTES;
             return 0;
         }
     }

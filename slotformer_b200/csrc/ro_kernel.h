@@ -27,9 +27,10 @@ struct ROParams {
     int fc;              // FFN hidden chunk (columns)
     int lmax;            // max window tokens over the rollout
     int lda, ldb;        // row strides (halves) of the fp16 activation buffers
-    int ln_smem;         // LayerNorm parameters staged in shared memory
+    int par_floats;      // per-layer parameter block (biases + LayerNorm) staged in smem
+    int par_double;      // 1: double-buffered (next layer prefetched), 0: single buffer (big shapes)
     int nstage;          // weight-panel ring depth
-    uint32_t off_h, off_a, off_b, off_bars, off_ring, off_ln;   // shared-memory byte offsets
+    uint32_t off_h, off_a, off_b, off_bars, off_ring, off_par;   // shared-memory byte offsets
     unsigned long long* prof;       // optional timeline buffer (debug)
     int prof_cap;
     ROLayer layer[RO_MAX_LAYERS];
@@ -37,6 +38,9 @@ struct ROParams {
 
 // fp32 [N][Kd] -> fp16 64x64 panels, 128B-swizzled (N, Kd multiples of 64)
 cudaError_t ro_pack_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st);
+// fp32 [N][Kd] -> fp16 128x64 weight tiles (pairs of swizzled 64x64 panels), rows padded to 128
+cudaError_t ro_pack2_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st);
+cudaError_t umma_test_launch(const __half* Wp, const float* X, float* out, int M, int N, int K, cudaStream_t st);
 // chooses hg / fc / buffer layout; returns 0 or -1 if the shape cannot be kept on chip
 int ro_plan(ROParams* p, int smem_limit, size_t* smem_bytes);
 cudaError_t ro_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st);

@@ -17,12 +17,16 @@ struct SAWeightsDev {
     const __half* w2;     // [D][Dm]
     const float *b_ih, *b_hh, *b1, *b2;
     const float *ln_q_w, *ln_q_b, *ln_m_w, *ln_m_b;
+    const float *ln_in_w, *ln_in_b;   // norm_inputs affine (applied here, not in the pass)
+    const float* wbeta;               // [D]  sum_c beta_c W_qk[c][:]  -> per-slot logit bias
 };
 
 // workspace carve-up (byte offsets), computed by sa_workspace_layout
 struct SAWorkspace {
-    size_t w_qk, w_iv, w_hh, w1, w2;   // each: hi then lo
-    size_t qt;         // [B][2][8][C] fp16
+    size_t w_qk, w_iv, w_hh, w1, w2;   // packed hi/lo panel pairs
+    size_t wbeta;      // [D] fp32
+    size_t qt;         // [B] x { hi [8][C] fp16, lo [8][C] fp16, logit bias [8] fp32 }
+    int qt_stride;     // halves per frame
     size_t partials;   // [B][nchunk][pstride] fp32
     size_t xsum;       // [B][C] fp32
     size_t xhat;       // [xhat_frames][N16/16][16*C] fp16 (swizzled 16-pixel tiles)
@@ -34,7 +38,7 @@ struct SAPassParams {
     const float* feats;
     long long feat_bstride;    // elements between frames
     __half* xhat;              // nullable when there is no later pass
-    const __half* qt;          // [B][2][8][C]
+    const __half* qt;          // per frame: hi [8][C], lo [8][C], 8 fp32 logit biases
     float* partials;
     float* seg_mask;           // nullable; written only by the last pass
     const float *ln_w, *ln_b;  // norm_inputs
@@ -52,7 +56,8 @@ struct SAUpdateParams {
     float* xsum;               // [B][C]; written when first != 0
     const float* slots_prev;   // [B][K][D] state before this update (slots_in or slots_out)
     float* slots_out;          // [B][K][D]
-    __half* qt;                // [B][2][8][C]; written when do_q != 0
+    __half* qt;                // see SAWorkspace::qt; written when do_q != 0
+    int qt_stride;
     int B, N, K, nchunk, pstride;
     int frame0, nframes;
     int do_update, do_q, first;
@@ -61,7 +66,8 @@ struct SAUpdateParams {
 
 void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, int n_iter, SAWorkspace* ws);
 cudaError_t sa_prep_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,
-                           const float* w_hh, const float* w1, const float* w2, char* ws_base,
+                           const float* w_hh, const float* w1, const float* w2, const float* ln_in_w,
+                           const float* ln_in_b, char* ws_base,
                            const SAWorkspace& ws, int C, int D, int DM, cudaStream_t st);
 cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, int smem_limit, cudaStream_t st);
 cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st);

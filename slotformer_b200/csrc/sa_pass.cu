@@ -38,6 +38,19 @@ bool sa_shape_supported(int C, int D, int DM) {
 // ============================================================================================
 // streaming pass
 // ============================================================================================
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2) on 64-bit register pairs
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
 template <int C, bool FIRST>
 struct PassCfg {
     static constexpr int KS = C / 16;
@@ -51,18 +64,12 @@ struct PassCfg {
     static constexpr int OFF_RED = PASS_WARPS * NST * STAGE_BYTES;
     static constexpr int RED_BYTES = 4 * NREG * 32 * 4;
     static constexpr int OFF_QF = OFF_RED + RED_BYTES;
-    static constexpr int QF_BYTES = 2 * 8 * C * 2;           // hi + lo
+    static constexpr int QF_BYTES = 2 * 8 * C * 2 + 32;      // hi + lo + 8 fp32 logit biases
     static constexpr int OFF_LN = OFF_QF + NQB * QF_BYTES;
-    static constexpr int OFF_CSW = OFF_LN + 2 * C * 4;
+    static constexpr int OFF_CSW = OFF_LN;
     static constexpr int OFF_BARS = OFF_CSW + 8 * 8 * 4;
     static constexpr int SMEM = OFF_BARS + PASS_WARPS * NST * 8;
 };
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int C, bool FIRST>
 __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassParams p) {
@@ -75,8 +82,6 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
     unsigned char* my_stages = smem + Cfg::OFF_STAGES + warp * NST * STAGE_BYTES;
     float* red = reinterpret_cast<float*>(smem + Cfg::OFF_RED);
     __half* qf = reinterpret_cast<__half*>(smem + Cfg::OFF_QF);
-    float* lng = reinterpret_cast<float*>(smem + Cfg::OFF_LN);
-    float* lnb = lng + C;
     float* colsum_w = reinterpret_cast<float*>(smem + Cfg::OFF_CSW);
     uint64_t* my_bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS) + warp * NST;
 
@@ -92,7 +97,6 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
         for (int s = 0; s < NST; ++s) mbar_init(&my_bars[s], 1);
         fence_mbar_init();
     }
-    if (FIRST) for (int i = tid; i < C; i += PASS_THREADS) { lng[i] = p.ln_w[i]; lnb[i] = p.ln_b[i]; }
     __syncthreads();
     if (my_items == 0) return;
 
@@ -129,8 +133,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
     auto load_qf = [&](int il, int buf, bool async) {
         const int item = (int)blockIdx.x + il * (int)gridDim.x;
         const int f = p.frame0 + item / p.nchunk;
-        const uint4* src = reinterpret_cast<const uint4*>(p.qt + (size_t)f * (2 * 8 * C));
-        uint4* dst = reinterpret_cast<uint4*>(qf + (size_t)buf * (2 * 8 * C));
+        const uint4* src = reinterpret_cast<const uint4*>(p.qt + (size_t)f * (Cfg::QF_BYTES / 2));
+        uint4* dst = reinterpret_cast<uint4*>(qf + (size_t)buf * (Cfg::QF_BYTES / 2));
         for (int i = tid; i < Cfg::QF_BYTES / 16; i += PASS_THREADS) {
             if (async) cp_async16(dst + i, src + i);
             else dst[i] = __ldg(src + i);
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
         const int item = (int)blockIdx.x + il * (int)gridDim.x;
         const int fl = item / p.nchunk, chunk = item % p.nchunk;
         const int f = p.frame0 + fl;
-        const __half* qh = qf + (size_t)((NQB == 2) ? (il & 1) : 0) * (2 * 8 * C);
+        const __half* qh = qf + (size_t)((NQB == 2) ? (il & 1) : 0) * (Cfg::QF_BYTES / 2);
         const __half* ql = qh + 8 * C;
         if (NQB == 2 && il + 1 < my_items) load_qf(il + 1, (il + 1) & 1, true);
 
@@ -165,13 +169,15 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
             bq_lo[ks][0] = *reinterpret_cast<const uint32_t*>(ql + g * C + c0);
             bq_lo[ks][1] = *reinterpret_cast<const uint32_t*>(ql + g * C + c0 + 8);
         }
+        const float lb0 = reinterpret_cast<const float*>(ql + 8 * C)[2 * t4];
+        const float lb1 = reinterpret_cast<const float*>(ql + 8 * C)[2 * t4 + 1];
         float uacc[KS][4];
 #pragma unroll
         for (int cb = 0; cb < KS; ++cb) { uacc[cb][0] = uacc[cb][1] = uacc[cb][2] = uacc[cb][3] = 0.f; }
         float cs0 = 0.f, cs1 = 0.f;
-        float xs[C / 32][4];
+        f32x2 xs2[C / 16];
 #pragma unroll
-        for (int i = 0; i < C / 32; ++i) { xs[i][0] = xs[i][1] = xs[i][2] = xs[i][3] = 0.f; }
+        for (int i = 0; i < C / 16; ++i) xs2[i] = pack2(0.f, 0.f);
         const bool s0ok = (2 * t4) < K, s1ok = (2 * t4 + 1) < K;
 
 #pragma unroll 1
@@ -186,55 +192,57 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
             mbar_wait(&my_bars[s], (n / NST) & 1);
             if (nvalid > 0 && !(p.dbg & 4)) {
                 if (FIRST) {
-                    // ---- LayerNorm 16 pixels in place: fp32 rows -> swizzled fp16 x^ tile ----
-                    // (x^ rows 8h..8h+7 land on raw rows 4h..4h+3, which are already in registers)
+                    // ---- normalise 16 pixels in place: fp32 rows -> swizzled fp16 t = (x-mu)*rstd ----
+                    // (the LayerNorm affine is folded into q~ and into the slot update; t rows 8h..8h+7
+                    //  land on raw rows 4h..4h+3, which are already in registers)
+                    if (nvalid < 16) {
+                        // ragged tail: zero the missing raw rows so they normalise to t = 0
+                        float4* z = reinterpret_cast<float4*>(stg + (size_t)nvalid * C * 4);
+                        for (int i = lane; i < (16 - nvalid) * (C / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        float4 v[2][C / 32];
+                        f32x2 v[2][C / 16];
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
                             const int row = 8 * hf + 4 * rr + pxi;
                             const float* tp = reinterpret_cast<const float*>(stg) + row * C + 4 * ch8;
 #pragma unroll
-                            for (int i = 0; i < C / 32; ++i)
-                                v[rr][i] = (row < nvalid) ? *reinterpret_cast<const float4*>(tp + 32 * i)
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int i = 0; i < C / 32; ++i) {
+                                const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tp + 32 * i);
+                                v[rr][2 * i] = q.x; v[rr][2 * i + 1] = q.y;
+                            }
                         }
                         __syncwarp();
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
                             const int row = 8 * hf + 4 * rr + pxi;
-                            const bool valid = row < nvalid;
-                            float sm = 0.f;
+                            f32x2 s2 = v[rr][0];
 #pragma unroll
-                            for (int i = 0; i < C / 32; ++i) sm += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
+                            for (int i = 1; i < C / 16; ++i) s2 = add2(s2, v[rr][i]);
+                            float sm = lo2(s2) + hi2(s2);
                             sm += __shfl_xor_sync(0xffffffffu, sm, 1);
                             sm += __shfl_xor_sync(0xffffffffu, sm, 2);
                             sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-                            const float mu = sm * (1.f / C);
-                            float qv = 0.f;
+                            const float nmu = -sm * (1.f / C);
+                            const f32x2 nmu2 = pack2(nmu, nmu);
+                            f32x2 q2 = pack2(0.f, 0.f);
 #pragma unroll
-                            for (int i = 0; i < C / 32; ++i) {
-                                v[rr][i].x -= mu; v[rr][i].y -= mu; v[rr][i].z -= mu; v[rr][i].w -= mu;
-                                qv = fmaf(v[rr][i].x, v[rr][i].x, qv); qv = fmaf(v[rr][i].y, v[rr][i].y, qv);
-                                qv = fmaf(v[rr][i].z, v[rr][i].z, qv); qv = fmaf(v[rr][i].w, v[rr][i].w, qv);
-                            }
+                            for (int i = 0; i < C / 16; ++i) { v[rr][i] = add2(v[rr][i], nmu2); q2 = fma2(v[rr][i], v[rr][i], q2); }
+                            float qv = lo2(q2) + hi2(q2);
                             qv += __shfl_xor_sync(0xffffffffu, qv, 1);
                             qv += __shfl_xor_sync(0xffffffffu, qv, 2);
                             qv += __shfl_xor_sync(0xffffffffu, qv, 4);
-                            const float rstd = valid ? rsqrtf(qv * (1.f / C) + LN_EPS) : 0.f;
+                            const float rstd = rsqrtf(qv * (1.f / C) + LN_EPS);
+                            const f32x2 r2 = pack2(rstd, rstd);
                             unsigned char* rowp = stg + row * ROWB + (ch8 & 1) * 8;
 #pragma unroll
                             for (int i = 0; i < C / 32; ++i) {
-                                const float4 gm = *reinterpret_cast<const float4*>(lng + 4 * ch8 + 32 * i);
-                                const float4 bt = *reinterpret_cast<const float4*>(lnb + 4 * ch8 + 32 * i);
-                                const float y0 = valid ? fmaf(v[rr][i].x * rstd, gm.x, bt.x) : 0.f;
-                                const float y1 = valid ? fmaf(v[rr][i].y * rstd, gm.y, bt.y) : 0.f;
-                                const float y2 = valid ? fmaf(v[rr][i].z * rstd, gm.z, bt.z) : 0.f;
-                                const float y3 = valid ? fmaf(v[rr][i].w * rstd, gm.w, bt.w) : 0.f;
-                                xs[i][0] += y0; xs[i][1] += y1; xs[i][2] += y2; xs[i][3] += y3;
+                                const f32x2 t0 = mul2(v[rr][2 * i], r2), t1 = mul2(v[rr][2 * i + 1], r2);
+                                xs2[2 * i] = add2(xs2[2 * i], t0); xs2[2 * i + 1] = add2(xs2[2 * i + 1], t1);
                                 const int chk = ((ch8 >> 1) + 4 * i) ^ (row & 7);
-                                uint2 pk; pk.x = pack_h2(y0, y1); pk.y = pack_h2(y2, y3);
+                                uint2 pk; pk.x = pack_h2(lo2(t0), hi2(t0)); pk.y = pack_h2(lo2(t1), hi2(t1));
                                 *reinterpret_cast<uint2*>(rowp + chk * 16) = pk;
                             }
                         }
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
                 }
                 const uint32_t tile_u32 = smem_u32(stg);
                 // ---- logits: 16 pixels x 8 slots, log2 domain (scale folded into q~) ----
-                float lgA[4] = {0.f, 0.f, 0.f, 0.f}, lgB[4] = {0.f, 0.f, 0.f, 0.f};
+                float lgA[4] = {lb0, lb1, lb0, lb1}, lgB[4] = {0.f, 0.f, 0.f, 0.f};
                 {
                     const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
                     const uint32_t rowa = tile_u32 + row * ROWB;
@@ -333,6 +341,12 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
         cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
         if (lane < 4) { colsum_w[warp * 8 + 2 * lane] = cs0; colsum_w[warp * 8 + 2 * lane + 1] = cs1; }
         if (FIRST) {
+            float xs[C / 32][4];
+#pragma unroll
+            for (int i = 0; i < C / 32; ++i) {
+                xs[i][0] = lo2(xs2[2 * i]); xs[i][1] = hi2(xs2[2 * i]);
+                xs[i][2] = lo2(xs2[2 * i + 1]); xs[i][3] = hi2(xs2[2 * i + 1]);
+            }
 #pragma unroll
             for (int i = 0; i < C / 32; ++i)
 #pragma unroll

@@ -35,7 +35,8 @@ __device__ __forceinline__ void store_packed(__half* dst, int kpt, int n, int k,
 __global__ void sa_prep_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
                                const float* __restrict__ wv, const float* __restrict__ w_ih,
                                const float* __restrict__ w_hh, const float* __restrict__ w1,
-                               const float* __restrict__ w2, __half* qk, __half* iv, __half* hh,
+                               const float* __restrict__ w2, const float* __restrict__ ln_w,
+                               const float* __restrict__ ln_b, __half* qk, __half* iv, __half* hh,
                                __half* p1, __half* p2, int C, int D, int DM, float qscale) {
     const int n_qk = C * D, n_iv = 3 * D * C, n_hh = 3 * D * D, n_1 = DM * D, n_2 = D * DM;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,7 +44,7 @@ __global__ void sa_prep_kernel(const float* __restrict__ wq, const float* __rest
         const int c = idx / D, e = idx % D;
         float acc = 0.f;
         for (int d = 0; d < D; ++d) acc = fmaf(wq[d * D + e], wk[d * C + c], acc);
-        store_packed(qk, D >> 6, c, e, acc * qscale);
+        store_packed(qk, D >> 6, c, e, acc * qscale * ln_w[c]);     // LayerNorm gamma folded in
     } else if ((idx -= n_qk) < n_iv) {      // W_iv[j][c] = sum_d W_ih[j][d] Wv[d][c]
         const int j = idx / C, c = idx % C;
         float acc = 0.f;
@@ -55,6 +56,26 @@ __global__ void sa_prep_kernel(const float* __restrict__ wq, const float* __rest
         store_packed(p1, D >> 6, idx / D, idx % D, w1[idx]);
     } else if ((idx -= n_1) < n_2) {
         store_packed(p2, DM >> 6, idx / DM, idx % DM, w2[idx]);
+    }
+}
+
+// wbeta[e] = qscale * sum_d Wq[d][e] (sum_c beta_c Wk[d][c]): the per-slot logit bias beta . q~[m]
+// equals LNq(S)[m] . wbeta.  One block; D <= 256.
+__global__ void sa_prep_wbeta_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
+                                     const float* __restrict__ ln_b, float* __restrict__ wbeta, int C,
+                                     int D, float qscale) {
+    __shared__ float tb[256];
+    const int t = threadIdx.x;
+    if (t < D) {
+        float a = 0.f;
+        for (int c = 0; c < C; ++c) a = fmaf(ln_b[c], wk[t * C + c], a);
+        tb[t] = a;
+    }
+    __syncthreads();
+    if (t < D) {
+        float a = 0.f;
+        for (int d = 0; d < D; ++d) a = fmaf(wq[d * D + t], tb[d], a);
+        wbeta[t] = a * qscale;
     }
 }
 
@@ -214,12 +235,13 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
             for (int r = warp; r < ROWS; r += UPD_WARPS) {
                 const int f = fbase + (r >> 3), slot = r & 7;
                 const bool ok = row_ok(r);
-                float den = 1.f;
+                float den = 1.f, csn = 0.f;
                 if (ok) {
                     float cs = 0.f;
                     for (int ch = 0; ch < p.nchunk; ++ch)
                         cs += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + 8 * C + slot);
-                    den = cs * (1.f / SA_PSCALE) + (float)N * p.eps;
+                    csn = cs * (1.f / SA_PSCALE);
+                    den = csn + (float)N * p.eps;
                 }
 #pragma unroll
                 for (int i = 0; i < C / 32; ++i) {
@@ -238,7 +260,11 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
                         } else {
                             xsv = p.xsum[(size_t)f * C + c];
                         }
-                        u = (us * (1.f / SA_PSCALE) + p.eps * xsv) / den;
+                        // t-statistics -> x^ statistics: x^ = gamma*t + beta
+                        const float gmc = __ldg(w.ln_in_w + c), btc = __ldg(w.ln_in_b + c);
+                        const float xs_hat = fmaf(gmc, xsv, (float)N * btc);
+                        const float us_hat = fmaf(gmc, us * (1.f / SA_PSCALE), btc * csn);
+                        u = (us_hat + p.eps * xs_hat) / den;
                         sprev = __ldg(p.slots_prev + ((size_t)f * K + slot) * D + c);
                     }
                     store_split(a_hi, a_lo, r * LDA + c, u);
@@ -346,6 +372,22 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
         // ---- q~ = LNq(S) W_qk^T -> fp16 hi/lo, rows >= K are zero ----
         if (Role::kConsumer) {
             ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, w.ln_q_w, w.ln_q_b, warp, lane);
+            __syncwarp();
+            // per-slot logit bias  beta . q~[m]  =  LNq(S)[m] . wbeta   (rows of this warp)
+            for (int r = warp; r < ROWS; r += UPD_WARPS) {
+                float a = 0.f;
+#pragma unroll
+                for (int i = 0; i < D / 32; ++i) {
+                    const int e = lane + 32 * i;
+                    a = fmaf(__half2float(a_hi[r * LDA + e]) + __half2float(a_lo[r * LDA + e]), __ldg(w.wbeta + e), a);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0 && fl0 + (r >> 3) < p.nframes) {
+                    float* lb = reinterpret_cast<float*>(p.qt + (size_t)(fbase + (r >> 3)) * p.qt_stride + 2 * 8 * C);
+                    lb[r & 7] = ((r & 7) < K) ? a : 0.f;
+                }
+            }
             R.sync();
         }
         for (int nb = 0; nb < C / 64; ++nb) {
@@ -362,7 +404,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
                         const int row = 16 * mb + g + 8 * (e >> 1), col = col0 + (e & 1);
                         if (fl0 + (row >> 3) < p.nframes) {
                             const float v = ((row & 7) < K) ? acc[mb][e] : 0.f;
-                            __half* qh = p.qt + (size_t)(fbase + (row >> 3)) * (2 * 8 * C) + (row & 7) * C + col;
+                            __half* qh = p.qt + (size_t)(fbase + (row >> 3)) * p.qt_stride + (row & 7) * C + col;
                             const __half hv = __float2half_rn(v);
                             qh[0] = hv;
                             qh[8 * C] = __float2half_rn(v - __half2float(hv));
@@ -409,6 +451,7 @@ void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, i
     ws->w_hh = take((size_t)3 * D * D * 2 * 2);
     ws->w1 = take((size_t)DM * D * 2 * 2);
     ws->w2 = take((size_t)D * DM * 2 * 2);
+    ws->wbeta = take((size_t)D * 4);
     // pixel chunking: 1024-pixel items (8 warps x 8 tiles), smaller for small N
     int chunk_px = 1024;
     while (chunk_px > 128 && chunk_px / 2 >= N) chunk_px /= 2;
@@ -416,7 +459,8 @@ void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, i
     ws->nchunk = (N + chunk_px - 1) / chunk_px;
     ws->n16 = ws->nchunk * chunk_px;
     ws->pstride = 9 * C + 8;
-    ws->qt = take((size_t)B * 2 * 8 * C * 2);
+    ws->qt_stride = 2 * 8 * C + 16;
+    ws->qt = take((size_t)B * ws->qt_stride * 2);
     ws->partials = take((size_t)B * ws->nchunk * ws->pstride * 4);
     ws->xsum = take((size_t)B * C * 4);
     ws->xhat_frames = (n_iter > 1) ? (chunk_frames < B ? chunk_frames : B) : 0;
@@ -425,13 +469,16 @@ void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, i
 }
 
 cudaError_t sa_prep_launch(const float* wq, const float* wk, const float* wv, const float* w_ih,
-                           const float* w_hh, const float* w1, const float* w2, char* base,
+                           const float* w_hh, const float* w1, const float* w2, const float* ln_in_w,
+                           const float* ln_in_b, char* base,
                            const SAWorkspace& ws, int C, int D, int DM, cudaStream_t st) {
     const int total = C * D + 3 * D * C + 3 * D * D + DM * D + D * DM;
     const float qscale = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
     auto H = [&](size_t off) { return reinterpret_cast<__half*>(base + off); };
-    sa_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(wq, wk, wv, w_ih, w_hh, w1, w2, H(ws.w_qk), H(ws.w_iv),
-                                                       H(ws.w_hh), H(ws.w1), H(ws.w2), C, D, DM, qscale);
+    sa_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(wq, wk, wv, w_ih, w_hh, w1, w2, ln_in_w, ln_in_b, H(ws.w_qk),
+                                                       H(ws.w_iv), H(ws.w_hh), H(ws.w1), H(ws.w2),
+                                                       C, D, DM, qscale);
+    sa_prep_wbeta_kernel<<<1, 256, 0, st>>>(wq, wk, ln_in_b, reinterpret_cast<float*>(base + ws.wbeta), C, D, qscale);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,9 @@ def load():
     lib.sfb_launch_count.restype = c.c_longlong
     lib.sfb_debug_set_profile.restype = None
     lib.sfb_debug_set_profile.argtypes = [c.c_void_p, c.c_int]
+    lib.sfb_debug_umma_gemm.restype = c.c_int
+    lib.sfb_debug_umma_gemm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int,
+                                        c.c_void_p, c.c_size_t, c.c_void_p]
     lib.sfb_sa_workspace_bytes.restype = c.c_size_t
     lib.sfb_sa_workspace_bytes.argtypes = [c.c_int] * 7
     lib.sfb_sa_forward.restype = c.c_int
@@ -93,9 +96,24 @@ def load():
 def exported_symbols():
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
     return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_debug_set_profile',
-            'sfb_sa_workspace_bytes',
+            'sfb_debug_umma_gemm', 'sfb_sa_workspace_bytes',
             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
             'sfb_rollout_forward']
+
+
+def umma_gemm(W, X):
+    """Self-test hook: X [N,K] @ W[M,K]^T on the tcgen05 path (fp16 operands, fp32 accumulate)."""
+    lib = load()
+    _require_cuda_f32('W', W)
+    _require_cuda_f32('X', X)
+    M, K = W.shape
+    N = X.shape[0]
+    out = torch.empty((N, M), dtype=torch.float32, device=W.device)
+    ws = torch.empty(M * K * 2, dtype=torch.uint8, device=W.device)
+    with torch.cuda.device(W.device):
+        _check(lib.sfb_debug_umma_gemm(W.contiguous().data_ptr(), X.contiguous().data_ptr(), out.data_ptr(),
+                                       M, N, K, ws.data_ptr(), ws.numel(), _stream(W.device)))
+    return out
 
 
 def launch_count():
