@@ -192,8 +192,11 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
 // ------------------------------------------------------------------------------------------
 // Rollout
 // ------------------------------------------------------------------------------------------
+static size_t pad128(int n) { return (size_t)((n + 127) / 128 * 128); }
+// packed fp16 weights; output-feature rows of every matrix are padded to multiples of 128
 static size_t ro_ws_elems(int Ds, int d, int F, int layers) {
-    return (size_t)d * Ds * 2 + (size_t)layers * ((size_t)3 * d * d + (size_t)d * d + (size_t)2 * F * d);
+    return pad128(d) * Ds + pad128(Ds) * d +
+           (size_t)layers * (pad128(3 * d) * d + pad128(d) * d + pad128(F) * d + pad128(d) * F);
 }
 
 size_t sfb_rollout_workspace_bytes(int Ds, int d, int F, int num_layers) {
@@ -215,9 +218,9 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
     struct Job { const float* src; size_t n; };
     cudaError_t e;
     auto run = [&](const float* src, int N_, int K_) -> int {
-        const size_t n = (size_t)N_ * K_;
+        const size_t n = pad128(N_) * K_;
         if (!src) return SFB_E_NULL;
-        e = sfb::ro_pack_launch(src, dst, N_, K_, st);
+        e = sfb::ro_pack2_launch(src, dst, N_, K_, st);
         if (e != cudaSuccess) return cuda_err(e);
         g_launches.fetch_add(1);
         dst += n;
@@ -257,16 +260,16 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     sfb::ROParams p{};
     p.hist = hist; p.pred = pred_out;
     const __half* ws = reinterpret_cast<const __half*>(workspace);
-    p.w_in = ws; ws += (size_t)d * Ds;
-    p.w_out = ws; ws += (size_t)Ds * d;
+    p.w_in = ws; ws += pad128(d) * Ds;
+    p.w_out = ws; ws += pad128(Ds) * d;
     p.b_in = w->in_proj_bias; p.b_out = w->out_proj_bias; p.pe = w->enc_pe;
     for (int l = 0; l < w->num_layers; ++l) {
         const sfb_ro_layer& s = w->layers[l];
         sfb::ROLayer& t = p.layer[l];
-        t.wqkv = ws; ws += (size_t)3 * d * d;
-        t.wo = ws; ws += (size_t)d * d;
-        t.w1 = ws; ws += (size_t)F * d;
-        t.w2 = ws; ws += (size_t)d * F;
+        t.wqkv = ws; ws += pad128(3 * d) * d;
+        t.wo = ws; ws += pad128(d) * d;
+        t.w1 = ws; ws += pad128(F) * d;
+        t.w2 = ws; ws += pad128(d) * F;
         t.bqkv = s.self_attn_in_proj_bias; t.bo = s.self_attn_out_proj_bias;
         t.b1 = s.linear1_bias; t.b2 = s.linear2_bias;
         t.ln1w = s.norm1_weight; t.ln1b = s.norm1_bias; t.ln2w = s.norm2_weight; t.ln2b = s.norm2_bias;
@@ -279,8 +282,16 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     p.lmax = p.cond_tokens;
     p.prof = g_prof; p.prof_cap = g_prof_cap;
     size_t smem = 0;
-    if (sfb::ro_plan(&p, di.smem_optin, &smem)) return SFB_E_BAD_SHAPE;
-    cudaError_t e = sfb::ro_launch(p, smem, reinterpret_cast<cudaStream_t>(stream));
+    // engine B (tcgen05 + TMEM) when the window fits on chip, else engine A (mma.sync); SFB_RO_ENGINE=mma forces A
+    const char* eng = getenv("SFB_RO_ENGINE");
+    const bool force_mma = eng && eng[0] == 'm';
+    cudaError_t e;
+    if (!force_mma && sfb::ro_umma_plan(&p, di.smem_optin, &smem) == 0) {
+        e = sfb::ro_umma_launch(p, smem, reinterpret_cast<cudaStream_t>(stream));
+    } else {
+        if (sfb::ro_mma_plan(&p, di.smem_optin, &smem)) return SFB_E_BAD_SHAPE;
+        e = sfb::ro_mma_launch(p, smem, reinterpret_cast<cudaStream_t>(stream));
+    }
     if (e != cudaSuccess) return cuda_err(e);
     g_launches.fetch_add(1);
     return SFB_OK;

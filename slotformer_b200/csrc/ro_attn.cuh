@@ -9,8 +9,8 @@ static constexpr int RO_THREADS = RO_WARPS * 32;
 static constexpr float RO_LN_EPS = 1e-5f;
 
 // LayerNorm rows [0, L) of h (fp32, stride d) -> fp16 rows of `out` (stride ldo); rows [L, Lp) = 0
-template <int DMODEL, int RPW>
-__device__ __forceinline__ void ln_to_half(const float* h, __half* out, int ldo, int L, int Lp,
+template <int DMODEL, int RPW, class Addr>
+__device__ __forceinline__ void ln_to_half(const float* h, unsigned char* out, Addr addr, int L, int Lp,
                                            const float* gw, const float* gb, int warp, int lane) {
     constexpr int PER0 = DMODEL / 32;
     float gmm[PER0], bta[PER0];
@@ -50,7 +50,8 @@ __device__ __forceinline__ void ln_to_half(const float* h, __half* out, int ldo,
             const float rstd = rsqrtf(q[j] * (1.f / DMODEL) + RO_LN_EPS);
 #pragma unroll
             for (int i = 0; i < PER; ++i)
-                out[r * ldo + lane + 32 * i] = __float2half_rn(r < L ? fmaf(v[j][i] * rstd, gmm[i], bta[i]) : 0.f);
+                *reinterpret_cast<__half*>(out + addr(r, lane + 32 * i)) =
+                    __float2half_rn(r < L ? fmaf(v[j][i] * rstd, gmm[i], bta[i]) : 0.f);
         }
     }
   }
@@ -58,8 +59,8 @@ __device__ __forceinline__ void ln_to_half(const float* h, __half* out, int ldo,
 
 // One (head, 16-query block) of softmax(Q K^T / sqrt(dh)) V.  Q/K/V live in `buf` (fp16, stride
 // ldb) at column offsets qcol/kcol/vcol; the result overwrites the Q block it came from.
-template <int DH, int NKB>
-__device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qcol, int kcol,
+template <int DH, int NKB, class Addr>
+__device__ __forceinline__ void attn_block(unsigned char* buf, Addr addr, int mb, int qcol, int kcol,
                                            int vcol, int L, int nkb, float sm_scale_log2, int lane) {
     const int g = lane >> 2, t4 = lane & 3;
     const uint32_t b_u32 = smem_u32(buf);
@@ -67,7 +68,7 @@ __device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qco
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) {
         const int row = 16 * mb + (lane & 7) + ((lane >> 3) & 1) * 8;
-        ldsm_x4(qf[ks], b_u32 + (uint32_t)(row * ldb + qcol + 16 * ks + (lane >> 4) * 8) * 2u);
+        ldsm_x4(qf[ks], b_u32 + addr(row, qcol + 16 * ks + (lane >> 4) * 8));
     }
     float s[NKB][4];
 #pragma unroll
@@ -79,7 +80,7 @@ __device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qco
             for (int ks = 0; ks < DH / 16; ++ks) {
                 uint32_t kf[4];
                 const int row = 8 * nb + (lane & 7) + (lane >> 4) * 8;
-                ldsm_x4(kf, b_u32 + (uint32_t)(row * ldb + kcol + 16 * ks + ((lane >> 3) & 1) * 8) * 2u);
+                ldsm_x4(kf, b_u32 + addr(row, kcol + 16 * ks + ((lane >> 3) & 1) * 8));
                 mma_f16(s[nb], qf[ks], kf[0], kf[1]);
                 mma_f16(s[nb + 1], qf[ks], kf[2], kf[3]);
             }
@@ -131,7 +132,7 @@ __device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qco
             for (int nb = 0; nb < DH / 8; nb += 2) {
                 uint32_t vf[4];
                 const int row = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
-                ldsm_x4_t(vf, b_u32 + (uint32_t)(row * ldb + vcol + 8 * nb + (lane >> 4) * 8) * 2u);
+                ldsm_x4_t(vf, b_u32 + addr(row, vcol + 8 * nb + (lane >> 4) * 8));
                 mma_f16(o[nb], a, vf[0], vf[1]);
                 mma_f16(o[nb + 1], a, vf[2], vf[3]);
             }
@@ -142,16 +143,16 @@ __device__ __forceinline__ void attn_block(__half* buf, int ldb, int mb, int qco
 #pragma unroll
     for (int nb = 0; nb < DH / 8; ++nb) {
         const int col = qcol + 8 * nb + 2 * t4;
-        *reinterpret_cast<__half2*>(buf + (16 * mb + g) * ldb + col) = __floats2half2_rn(o[nb][0] * i0, o[nb][1] * i0);
-        *reinterpret_cast<__half2*>(buf + (16 * mb + g + 8) * ldb + col) = __floats2half2_rn(o[nb][2] * i1, o[nb][3] * i1);
+        *reinterpret_cast<__half2*>(buf + addr(16 * mb + g, col)) = __floats2half2_rn(o[nb][0] * i0, o[nb][1] * i0);
+        *reinterpret_cast<__half2*>(buf + addr(16 * mb + g + 8, col)) = __floats2half2_rn(o[nb][2] * i1, o[nb][3] * i1);
     }
 }
 
 // All (<= NMB) 16-query blocks of one head in one go: K/V fragments are loaded once and the
 // independent per-block chains (MMA -> shuffles -> exp2 -> MMA) interleave.  Used when the window
 // is short (NMB * NKB accumulators fit in registers).
-template <int DH, int NKB, int NMB>
-__device__ __forceinline__ void attn_head(__half* buf, int ldb, int nmb, int qcol, int kcol, int vcol,
+template <int DH, int NKB, int NMB, class Addr>
+__device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb, int qcol, int kcol, int vcol,
                                           int L, int nkb, float sm_scale_log2, int lane) {
     const int g = lane >> 2, t4 = lane & 3;
     const uint32_t b_u32 = smem_u32(buf);
@@ -161,7 +162,7 @@ __device__ __forceinline__ void attn_head(__half* buf, int ldb, int nmb, int qco
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks) {
             const int row = 16 * (mb < nmb ? mb : 0) + (lane & 7) + ((lane >> 3) & 1) * 8;
-            ldsm_x4(qf[mb][ks], b_u32 + (uint32_t)(row * ldb + qcol + 16 * ks + (lane >> 4) * 8) * 2u);
+            ldsm_x4(qf[mb][ks], b_u32 + addr(row, qcol + 16 * ks + (lane >> 4) * 8));
         }
     float s[NMB][NKB][4];
 #pragma unroll
@@ -175,7 +176,7 @@ __device__ __forceinline__ void attn_head(__half* buf, int ldb, int nmb, int qco
             for (int ks = 0; ks < DH / 16; ++ks) {
                 uint32_t kf[4];
                 const int row = 8 * nb + (lane & 7) + (lane >> 4) * 8;
-                ldsm_x4(kf, b_u32 + (uint32_t)(row * ldb + kcol + 16 * ks + ((lane >> 3) & 1) * 8) * 2u);
+                ldsm_x4(kf, b_u32 + addr(row, kcol + 16 * ks + ((lane >> 3) & 1) * 8));
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb) {
                     mma_f16(s[mb][nb], qf[mb][ks], kf[0], kf[1]);
@@ -246,7 +247,7 @@ __device__ __forceinline__ void attn_head(__half* buf, int ldb, int nmb, int qco
             for (int nb = 0; nb < DH / 8; nb += 2) {
                 uint32_t vf[4];
                 const int row = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
-                ldsm_x4_t(vf, b_u32 + (uint32_t)(row * ldb + vcol + 8 * nb + (lane >> 4) * 8) * 2u);
+                ldsm_x4_t(vf, b_u32 + addr(row, vcol + 8 * nb + (lane >> 4) * 8));
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb) {
                     const uint32_t a[4] = {pf[mb][2 * kk][0], pf[mb][2 * kk][1], pf[mb][2 * kk + 1][0], pf[mb][2 * kk + 1][1]};
@@ -264,8 +265,8 @@ __device__ __forceinline__ void attn_head(__half* buf, int ldb, int nmb, int qco
 #pragma unroll
             for (int nb = 0; nb < DH / 8; ++nb) {
                 const int col = qcol + 8 * nb + 2 * t4;
-                *reinterpret_cast<__half2*>(buf + (16 * mb + g) * ldb + col) = __floats2half2_rn(o_[mb][nb][0] * i0, o_[mb][nb][1] * i0);
-                *reinterpret_cast<__half2*>(buf + (16 * mb + g + 8) * ldb + col) = __floats2half2_rn(o_[mb][nb][2] * i1, o_[mb][nb][3] * i1);
+                *reinterpret_cast<__half2*>(buf + addr(16 * mb + g, col)) = __floats2half2_rn(o_[mb][nb][0] * i0, o_[mb][nb][1] * i0);
+                *reinterpret_cast<__half2*>(buf + addr(16 * mb + g + 8, col)) = __floats2half2_rn(o_[mb][nb][2] * i1, o_[mb][nb][3] * i1);
             }
         }
     }

@@ -25,28 +25,6 @@ static constexpr int RO_PANEL_BYTES = 64 * 64 * 2;      // one 64(n) x 64(k) fp1
 static constexpr int RO_PANEL_HALVES = 64 * 64;
 
 // ----------------------------------------------------------------------------
-// weight preparation: fp32 [N][Kd] -> fp16 panels (nb-major, kb-minor), 128B-swizzled rows
-// ----------------------------------------------------------------------------
-__global__ void ro_pack_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int Kd) {
-    const size_t total = (size_t)N * Kd;
-    const int kpt = Kd >> 6;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i / Kd), k = (int)(i % Kd);
-        const int nb = n >> 6, r = n & 63, kb = k >> 6, kk = k & 63;
-        const size_t off = ((size_t)nb * kpt + kb) * RO_PANEL_HALVES + r * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
-        dst[off] = __float2half_rn(src[i]);
-    }
-}
-
-cudaError_t ro_pack_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st) {
-    const size_t n = (size_t)N * Kd;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 1184) blocks = 1184;
-    ro_pack_kernel<<<blocks, 256, 0, st>>>(src, dst, N, Kd);
-    return cudaGetLastError();
-}
-
-// ----------------------------------------------------------------------------
 // GEMM over a sub-block of a packed weight matrix
 // ----------------------------------------------------------------------------
 struct GemmOp {
@@ -74,7 +52,7 @@ struct Producer {
         mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
         mbar_arrive_expect_tx(&ring.full[s], RO_PANEL_BYTES);
         bulk_g2s(ring.stages + (size_t)s * RO_PANEL_BYTES,
-                 op.base + ((size_t)(op.nb0 + nb) * op.kpt + op.kb0 + kb) * RO_PANEL_HALVES,
+                 op.base + (((size_t)((op.nb0 + nb) >> 1) * op.kpt + op.kb0 + kb) * 2 + ((op.nb0 + nb) & 1)) * RO_PANEL_HALVES,
                  RO_PANEL_BYTES, &ring.full[s], pol);
         ++pidx;
     }
@@ -178,6 +156,8 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
     const int hgw = HG * DH;
     const float sm_scale_log2 = rsqrtf((float)DH) * 1.4426950408889634f;
     auto no_pre = [](int) { return make_float2(0.f, 0.f); };
+    auto addr_a = [=](int r, int c) { return (uint32_t)((r * lda + c) * 2); };
+    auto addr_b = [=](int r, int c) { return (uint32_t)((r * ldb + c) * 2); };
     const int PF = p.par_floats;
     // per-layer parameter block in smem: bqkv[3d] bo[d] b1[F] b2[d] ln1w ln1b ln2w ln2b [d each]
     auto load_params = [&](int layer, int buf) {
@@ -259,7 +239,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                 const float* l2b = l1w + 3 * DMODEL;
                 if (Role::kConsumer && p.par_double) load_params((layer + 1) % p.layers, (lcount + 1) & 1);   // prefetch next layer
                 if (Role::kConsumer) {
-                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, abuf, lda, L, Lp, l1w, l1b, warp, lane);
+                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, reinterpret_cast<unsigned char*>(abuf), addr_a, L, Lp, l1w, l1b, warp, lane);
                     R.sync();
                 }
                 stamp();   // LN1 done
@@ -290,11 +270,11 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                         if (NKB <= 6) {
                             for (int hh = warp; hh < HG; hh += RO_WARPS)
                                 attn_head<DH, (NKB <= 6 ? NKB : 2), (NKB <= 6 ? NKB / 2 : 1)>(
-                                    bbuf, ldb, nmb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb, sm_scale_log2, lane);
+                                    reinterpret_cast<unsigned char*>(bbuf), addr_b, nmb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb, sm_scale_log2, lane);
                         } else {
                             for (int item = warp; item < HG * nmb; item += RO_WARPS) {
                                 const int hh = item / nmb, mb = item % nmb;
-                                attn_block<DH, NKB>(bbuf, ldb, mb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb,
+                                attn_block<DH, NKB>(reinterpret_cast<unsigned char*>(bbuf), addr_b, mb, hh * DH, hgw + hh * DH, 2 * hgw + hh * DH, L, nkb,
                                                     sm_scale_log2, lane);
                             }
                         }
@@ -317,7 +297,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
                 }
                 // ---- y = LN2(h);  h += W2 relu(W1 y + b1) + b2, FC hidden columns at a time ----
                 if (Role::kConsumer) {
-                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, abuf, lda, L, Lp, l2w, l2b, warp, lane);
+                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, reinterpret_cast<unsigned char*>(abuf), addr_a, L, Lp, l2w, l2b, warp, lane);
                     R.sync();
                 }
                 stamp();   // LN2 done
@@ -378,7 +358,7 @@ __device__ __forceinline__ void run_rollout(Role& R, const ROParams& p, float* h
 }
 
 template <int DMODEL, int DH, int NKB>
-__global__ void __launch_bounds__(RO_THREADS + 32, 1) ro_forward_kernel(const ROParams p) {
+__global__ void __launch_bounds__(RO_THREADS + 32, 1) ro_mma_forward_kernel(const ROParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* h = reinterpret_cast<float*>(smem + p.off_h);        // [Lmax_p][DMODEL]
     __half* abuf = reinterpret_cast<__half*>(smem + p.off_a);   // [Lmax_p][lda]
@@ -408,7 +388,7 @@ __global__ void __launch_bounds__(RO_THREADS + 32, 1) ro_forward_kernel(const RO
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
-int ro_plan(ROParams* p, int smem_limit, size_t* smem_bytes) {
+int ro_mma_plan(ROParams* p, int smem_limit, size_t* smem_bytes) {
     const int d = p->d, Ds = p->Ds, F = p->F;
     if (!(d == 128 || d == 256)) return -1;
     if (p->heads < 1 || d % p->heads) return -1;
@@ -453,14 +433,14 @@ int ro_plan(ROParams* p, int smem_limit, size_t* smem_bytes) {
 
 template <int DMODEL, int DH, int NKB>
 static cudaError_t ro_launch_t(const ROParams& p, size_t smem_bytes, cudaStream_t st) {
-    auto kern = ro_forward_kernel<DMODEL, DH, NKB>;
+    auto kern = ro_mma_forward_kernel<DMODEL, DH, NKB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<p.B, RO_THREADS + 32, smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t ro_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st) {
+cudaError_t ro_mma_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st) {
     const int Lp = (p.lmax + 15) & ~15;
     if (p.d == 128) {
         if (Lp <= 48) return ro_launch_t<128, 16, 6>(p, smem_bytes, st);

@@ -36,13 +36,15 @@ struct ROParams {
     ROLayer layer[RO_MAX_LAYERS];
 };
 
-// fp32 [N][Kd] -> fp16 64x64 panels, 128B-swizzled (N, Kd multiples of 64)
-cudaError_t ro_pack_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st);
 // fp32 [N][Kd] -> fp16 128x64 weight tiles (pairs of swizzled 64x64 panels), rows padded to 128
 cudaError_t ro_pack2_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st);
 cudaError_t umma_test_launch(const __half* Wp, const float* X, float* out, int M, int N, int K, cudaStream_t st);
 // chooses hg / fc / buffer layout; returns 0 or -1 if the shape cannot be kept on chip
-int ro_plan(ROParams* p, int smem_limit, size_t* smem_bytes);
-cudaError_t ro_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st);
+// engine A (mma.sync from a TMA-fed panel ring; any supported shape)
+int ro_mma_plan(ROParams* p, int smem_limit, size_t* smem_bytes);
+cudaError_t ro_mma_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st);
+// engine B (tcgen05 + TMEM, swap-AB; windows up to 64 tokens that fit on chip)
+int ro_umma_plan(ROParams* p, int smem_limit, size_t* smem_bytes);
+cudaError_t ro_umma_launch(const ROParams& p, size_t smem_bytes, cudaStream_t st);
 
 }  // namespace sfb

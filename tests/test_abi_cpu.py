@@ -48,6 +48,9 @@ def test_workspace_sizes(lib):
     d, Ds, F, L = 128, 128, 512, 4
     want = (2 * d * Ds + L * (3 * d * d + d * d + 2 * F * d)) * 2
     assert lib.sfb_rollout_workspace_bytes(Ds, d, F, L) == want
+    # output-feature rows are padded to multiples of 128 (out_proj with Ds = 192 -> 256 rows)
+    assert lib.sfb_rollout_workspace_bytes(192, 256, 1024, 8) == \
+        (256 * 192 + 256 * 256 + 8 * (768 * 256 + 256 * 256 + 2 * 1024 * 256)) * 2
 
 
 def test_null_and_shape_validation_without_gpu(lib):
