@@ -42,6 +42,12 @@ WORKLOAD = ('OBJ3D SlotFormer rollout, B=64, 128x128 (64x64 feature grid), K=6, 
             'SlotAttention(384 frames x 4096 x 128, 2 it) + SlotRollouter(d=128, 4L, 8H, F=512, 10 steps)')
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum over the kernels of ONE sfb_sa_forward call on this
+# workload, from the ncu --set full capture summarised in profiles/ (None until captured)
+SA_TRAFFIC_BYTES = None
+SA_TRAFFIC_SOURCE = None
+
+
 def sa_bytes_per_frame():
     return WL['N'] * WL['C'] * 4 + 2 * WL['K'] * WL['D'] * 4
 
@@ -339,11 +345,13 @@ def run_ours(args):
                    'l2': 'no flush needed: each step streams 805 MB of features (> 126 MB L2)',
                    'per_gpu_clips': B, 'parallelism': f'clip-sharded x{world}, no data-path collective'},
         'clocks': clocks, 'gpu_launches': int(launches),
-        'roofline': {'kernel': 'sa_forward_kernel', 'bound': 'hbm', 'achieved': sa_gbs, 'peak': pk['hbm'],
-                     'unit': 'GB/s', 'frac': sa_gbs / pk['hbm'], 'traffic': None,
+        'roofline': {'kernel': 'sfb_sa_forward: sa_prep + sa_update x3 + sa_pass<first> + sa_pass<next>',
+                     'bound': 'hbm', 'achieved': sa_gbs, 'peak': pk['hbm'],
+                     'unit': 'GB/s', 'frac': sa_gbs / pk['hbm'], 'traffic': SA_TRAFFIC_BYTES,
+                     'traffic_source': SA_TRAFFIC_SOURCE,
                      'ms_per_launch': sa_ms, 'peak_source': pk['src'],
                      'algorithmic_bytes_per_launch': frames * sa_bytes_per_frame()},
-        'roofline_rollout': {'kernel': 'ro_forward_kernel', 'bound': 'tensor', 'achieved': ro_tf,
+        'roofline_rollout': {'kernel': 'ro_umma_forward_kernel (tcgen05)', 'bound': 'tensor', 'achieved': ro_tf,
                              'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ro_tf / pk['tf'],
                              'ms_per_launch': ro_ms, 'flops_per_launch': ro_flops_total()},
     }

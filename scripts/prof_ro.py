@@ -25,10 +25,7 @@ t = buf.cpu().numpy(); n = int((t != 0).sum()); t = t[:n].astype(np.float64)
 per_step = n // WL['T_out']
 T = t[:per_step * WL['T_out']].reshape(WL['T_out'], per_step)
 d = np.diff(T, axis=1).mean(0) / 1e3
-names = ['in_proj'] + ['LN1', 'qkv', 'attn', 'outproj', 'LN2', 'ffn1a', 'ffn2a', 'ffn1b', 'ffn2b'] * WL['layers']
+d = np.diff(T, axis=1).mean(0) / 1e3
 print('stamps/step', per_step, 'step period us', np.diff(T[:, 0]).mean() / 1e3)
-print('in_proj', round(d[0], 2))
-L = (per_step - 2) // WL['layers']
-for l in range(WL['layers']):
-    print('layer', l, [f'{names[1 + j]}={d[1 + l * L + j]:.2f}' for j in range(L)])
-print('tail (out_proj + loop) us', (np.diff(T[:, 0]).mean() - (T[:, -1] - T[:, 0]).mean()) / 1e3)
+print('deltas (us):', np.round(d, 2).tolist())
+print('tail us', (np.diff(T[:, 0]).mean() - (T[:, -1] - T[:, 0]).mean()) / 1e3)

@@ -281,6 +281,7 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     p.pe_tokens = p.cond_tokens;
     p.lmax = p.cond_tokens;
     p.prof = g_prof; p.prof_cap = g_prof_cap;
+    { const char* dv = getenv("SFB_DBG"); p.dbg = dv ? atoi(dv) : 0; }
     size_t smem = 0;
     // engine B (tcgen05 + TMEM) when the window fits on chip, else engine A (mma.sync); SFB_RO_ENGINE=mma forces A
     const char* eng = getenv("SFB_RO_ENGINE");

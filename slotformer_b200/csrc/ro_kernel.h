@@ -33,6 +33,7 @@ struct ROParams {
     uint32_t off_h, off_a, off_b, off_bars, off_ring, off_par;   // shared-memory byte offsets
     unsigned long long* prof;       // optional timeline buffer (debug)
     int prof_cap;
+    int dbg;             // SFB_DBG switches (engine B): 1 = no weight copies, 2 = no MMAs, 4 = no epilogue math
     ROLayer layer[RO_MAX_LAYERS];
 };
 

@@ -45,12 +45,14 @@ struct BProducer {
     BRing ring;
     uint32_t pidx;
     uint64_t pol;
+    int dbg;
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) {
         for (int t = 0; t < op.ntile; ++t)
             for (int kb = 0; kb < op.nkb; ++kb, ++pidx) {
                 const int s = pidx % ring.nstage;
                 mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+                if (dbg & 1) { mbar_arrive(&ring.full[s]); continue; }
                 mbar_arrive_expect_tx(&ring.full[s], RU_TILE_BYTES);
                 bulk_g2s(ring.stages + (size_t)s * RU_TILE_BYTES,
                          op.base + ((size_t)(op.tile0 + t) * op.kpt + op.kb0 + kb) * RU_TILE_HALVES,
@@ -67,6 +69,7 @@ struct BMma {
     uint32_t tmem;
     uint64_t* accfull;
     int lane;
+    int dbg;
     // b_u32: smem address of the token operand (k-block 0), kblock_bytes apart per 64 k
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, Pre, Epi) {
@@ -78,6 +81,7 @@ struct BMma {
                     mbar_wait(&ring.full[s], (pidx / ring.nstage) & 1);
                     tcgen05_fence_after();
                     const uint32_t a_u32 = smem_u32(ring.stages + (size_t)s * RU_TILE_BYTES);
+                    if (!(dbg & 2))
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
                         umma_f16(tmem + (uint32_t)(t * ntok), umma_smem_desc(a_u32 + k4 * 32),
@@ -100,7 +104,8 @@ struct BCompute {
     uint64_t* accfull;
     uint32_t ngemm;
     int warp, lane;
-    // epi(feature, token, value, pre(feature)) for every accumulator element of this warp:
+    int dbg;
+    // epi(feature, token8, values[8], pre(feature)): 8 consecutive tokens (token8 % 8 == 0) of one feature;
     // features of the warp's TMEM lane quadrant, one half of the tokens (warps w and w+4 share lanes)
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int ntok, Pre pre, Epi epi) {
@@ -108,7 +113,7 @@ struct BCompute {
         ++ngemm;
         tcgen05_fence_after();
         const int q = warp & 3, half = ntok >> 1, t0 = (warp >> 2) * half;
-        for (int t = 0; t < op.ntile; ++t) {
+        for (int t = 0; t < ((dbg & 4) ? 0 : op.ntile); ++t) {
             const int f = t * 128 + 32 * q + lane;
             const float pv = pre(f);
             const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * ntok + t0);
@@ -118,12 +123,8 @@ struct BCompute {
                 const bool two = (c0 + 8) < half;
                 if (two) tmem_ld8(ta + c0 + 8, v1);
                 tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) epi(f, t0 + c0 + i, v0[i], pv);
-                if (two) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) epi(f, t0 + c0 + 8 + i, v1[i], pv);
-                }
+                epi(f, t0 + c0, v0, pv);                 // 8 consecutive tokens, base a multiple of 8
+                if (two) epi(f, t0 + c0 + 8, v1, pv);
             }
         }
         tcgen05_fence_before();
@@ -156,6 +157,9 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
         }
         cp_async_commit();
     };
+    int pidx_prof = 0;
+    const bool do_prof = Role::kCompute && (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+    auto stamp = [&]() { if (do_prof && pidx_prof < p.prof_cap) p.prof[pidx_prof++] = globaltimer_ns(); };
     uint32_t lcount = 0;
     if (Role::kCompute) { load_params(0, 0); cp_async_wait_all(); }
     R.sync();
@@ -170,6 +174,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
             else { L = total < p.cond_tokens ? total : p.cond_tokens; base = total - L; pe0 = p.pe_tokens - L; }
             const int Lp = (L + 15) & ~15, nmb = Lp >> 4, nkb = Lp >> 3;
 
+            stamp();   // 0 step start
             if (Role::kCompute) {
                 for (int i = tid; i < Lp * (Ds / 4); i += RO_THREADS) {
                     const int r = i / (Ds / 4), c4 = (i % (Ds / 4)) * 4;
@@ -190,11 +195,16 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 const UOp op{p.w_in, Ds >> 6, 0, DMODEL >> 7, 0, Ds >> 6};
                 R.gemm(op, x_u32, kbb, Lp,
                        [&](int f) { return __ldg(p.b_in + f); },
-                       [&](int f, int t, float v, float bi) {
-                           h[t * DMODEL + f] = (t < L) ? v + bi + __ldg(p.pe + (size_t)(pe0 + t) * DMODEL + f) : 0.f;
+                       [&](int f, int t8, const float (&v)[8], float bi) {
+#pragma unroll
+                           for (int i = 0; i < 8; ++i) {
+                               const int t = t8 + i;
+                               h[t * DMODEL + f] = (t < L) ? v[i] + bi + __ldg(p.pe + (size_t)(pe0 + t) * DMODEL + f) : 0.f;
+                           }
                        });
             }
             R.sync();
+            stamp();   // in_proj done
 
             for (int layer = 0; layer < p.layers; ++layer) {
                 const ROLayer& ly = p.layer[layer];
@@ -216,16 +226,22 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                     ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
                 }
                 R.sync();
+                stamp();   // LN1
                 // ---- packed q | k | v projection -> Y[token][3d] ----
                 {
                     const UOp op{ly.wqkv, DMODEL >> 6, 0, (3 * DMODEL) >> 7, 0, DMODEL >> 6};
                     R.gemm(op, x_u32, kbb, Lp,
                            [&](int f) { return s_bqkv[f]; },
-                           [&](int f, int t, float v, float bi) {
-                               *reinterpret_cast<__half*>(yb + addr_s(t, f)) = __float2half_rn(v + bi);
+                           [&](int f, int t8, const float (&v)[8], float bi) {
+                               unsigned char* yf = yb + (f >> 6) * kbb + t8 * 128 + (f & 7) * 2;
+                               const int chunk = (f & 63) >> 3;
+#pragma unroll
+                               for (int i = 0; i < 8; ++i)
+                                   *reinterpret_cast<__half*>(yf + i * 128 + ((chunk ^ i) << 4)) = __float2half_rn(v[i] + bi);
                            });
                 }
                 R.sync();
+                stamp();   // qkv
                 if (Role::kCompute) {
                     if (NKB <= 6) {
                         for (int hh = warp; hh < p.heads; hh += RO_WARPS)
@@ -240,17 +256,24 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                     }
                 }
                 R.sync();
+                stamp();   // attn
                 // ---- h += O Wo^T + bo ----
                 {
                     const UOp op{ly.wo, DMODEL >> 6, 0, DMODEL >> 7, 0, DMODEL >> 6};
                     R.gemm(op, y_u32, kbb, Lp,
                            [&](int f) { return s_bo[f]; },
-                           [&](int f, int t, float v, float bi) { h[t * DMODEL + f] += v + bi; });
+                           [&](int f, int t8, const float (&v)[8], float bi) {
+                               float* hf = h + t8 * DMODEL + f;
+#pragma unroll
+                               for (int i = 0; i < 8; ++i) hf[i * DMODEL] += v[i] + bi;
+                           });
                 }
                 R.sync();
+                stamp();   // outproj
                 if (Role::kCompute)
                     ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l2w, l2b, warp, lane);
                 R.sync();
+                stamp();   // LN2
                 // ---- h += W2 relu(W1 y + b1) + b2, FC hidden features at a time ----
                 for (int f0 = 0; f0 < F; f0 += FC) {
                     const int fcw = (F - f0) < FC ? (F - f0) : FC;
@@ -258,20 +281,30 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                         const UOp op{ly.w1, DMODEL >> 6, f0 >> 7, fcw >> 7, 0, DMODEL >> 6};
                         R.gemm(op, x_u32, kbb, Lp,
                                [&](int f) { return s_b1[f0 + f]; },
-                               [&](int f, int t, float v, float bi) {
-                                   *reinterpret_cast<__half*>(yb + addr_s(t, f)) = __float2half_rn(fmaxf(v + bi, 0.f));
-                               });
+                               [&](int f, int t8, const float (&v)[8], float bi) {
+                               unsigned char* yf = yb + (f >> 6) * kbb + t8 * 128 + (f & 7) * 2;
+                               const int chunk = (f & 63) >> 3;
+#pragma unroll
+                               for (int i = 0; i < 8; ++i)
+                                   *reinterpret_cast<__half*>(yf + i * 128 + ((chunk ^ i) << 4)) = __float2half_rn(fmaxf(v[i] + bi, 0.f));
+                           });
                     }
                     R.sync();
+                    stamp();   // ffn1
                     const bool first = (f0 == 0);
                     {
                         const UOp op{ly.w2, F >> 6, 0, DMODEL >> 7, f0 >> 6, fcw >> 6};
                         R.gemm(op, y_u32, kbb, Lp,
                                [&](int f) { return first ? s_b2[f] : 0.f; },
-                               [&](int f, int t, float v, float bi) { h[t * DMODEL + f] += v + bi; });
+                               [&](int f, int t8, const float (&v)[8], float bi) {
+                               float* hf = h + t8 * DMODEL + f;
+#pragma unroll
+                               for (int i = 0; i < 8; ++i) hf[i * DMODEL] += v[i] + bi;
+                           });
                     }
                     if (Role::kCompute && p.par_double && f0 + FC >= F) cp_async_wait_all();
                     R.sync();
+                    stamp();   // ffn2
                 }
                 ++lcount;
             }
@@ -289,8 +322,10 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 const UOp op{p.w_out, DMODEL >> 6, 0, (Ds + 127) >> 7, 0, DMODEL >> 6};
                 R.gemm(op, x_u32, kbb, 16,
                        [&](int f) { return f < Ds ? __ldg(p.b_out + f) : 0.f; },
-                       [&](int f, int t, float v, float bi) {
-                           if (t < K && f < Ds) dst[(size_t)t * Ds + f] = v + bi;
+                       [&](int f, int t8, const float (&v)[8], float bi) {
+#pragma unroll
+                           for (int i = 0; i < 8; ++i)
+                               if (t8 + i < K && f < Ds) dst[(size_t)(t8 + i) * Ds + f] = v[i] + bi;
                        });
             }
             R.sync();   // pred_out[step] visible to this CTA's next window load
@@ -324,14 +359,14 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ro_umma_forward_kernel(const RO
 
     if (warp == RO_WARPS) {
         if (lane == 0) {
-            BProducer P{ring, 0u, l2_policy_evict_last()};
+            BProducer P{ring, 0u, l2_policy_evict_last(), p.dbg};
             run_rollout_b<DMODEL, DH, NKB>(P, p, h, xb, yb, par, tid, warp, lane);
         }
     } else if (warp == RO_WARPS + 1) {
-        BMma M{ring, 0u, tmem, accfull, lane};
+        BMma M{ring, 0u, tmem, accfull, lane, p.dbg};
         run_rollout_b<DMODEL, DH, NKB>(M, p, h, xb, yb, par, tid, warp, lane);
     } else {
-        BCompute C{tmem, accfull, 0u, warp, lane};
+        BCompute C{tmem, accfull, 0u, warp, lane, p.dbg};
         run_rollout_b<DMODEL, DH, NKB>(C, p, h, xb, yb, par, tid, warp, lane);
     }
     tcgen05_fence_before();
