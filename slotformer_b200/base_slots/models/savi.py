@@ -1,0 +1,262 @@
+"""SAVi / StoSAVi video slot model -- the caller of hot path 1.
+
+Same constructor, attributes, ``state_dict`` keys and methods as reference ``StoSAVi``
+(slotformer/base_slots/models/savi.py:113-546): CNN encoder -> per-frame Slot Attention
+(``self.slot_attention``, the sm_100a kernels) with slots carried through the predictor ->
+optional spatial-broadcast decoder.  Encoder / predictor / decoder are stock PyTorch (cuDNN);
+they are "next" rows f1-f3 of SURVEY.md section 8, not kernel targets of this round.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ...compat.nerv.models import conv_norm_act, deconv_norm_act, deconv_out_shape
+from ...compat.nerv.training import BaseModel
+from .predictor import ResidualMLPPredictor, RNNPredictorWrapper, TransformerPredictor
+from .slot_attention import SlotAttention
+from .utils import SoftPositionEmbed, assert_shape, torch_cat
+
+
+def build_broadcast_decoder(owner):
+    """Creates ``owner.decoder`` / ``owner.decoder_pos_embedding`` from ``owner.dec_dict``
+    (shared by StoSAVi and SlotFormer, reference savi.py:255-293)."""
+    cfg = owner.dec_dict
+    owner.dec_channels = cfg['dec_channels']
+    owner.dec_resolution = cfg['dec_resolution']
+    owner.dec_ks = cfg['dec_ks']
+    owner.dec_norm = cfg['dec_norm']
+    assert owner.dec_channels[0] == owner.slot_size, 'wrong in_channels for Decoder'
+    blocks, size, stride = [], owner.dec_resolution[0], 2
+    for cin, cout in zip(owner.dec_channels[:-1], owner.dec_channels[1:]):
+        if size == owner.resolution[0]:
+            stride = 1          # target size reached: remaining blocks keep the resolution
+        blocks.append(deconv_norm_act(cin, cout, kernel_size=owner.dec_ks, stride=stride,
+                                      norm=owner.dec_norm, act='relu'))
+        size = deconv_out_shape(size, stride, owner.dec_ks // 2, owner.dec_ks, stride - 1)
+    assert_shape(owner.resolution, (size, size),
+                 message='Output shape of decoder did not match input resolution. '
+                         'Try changing `decoder_resolution`.')
+    blocks.append(nn.Conv2d(owner.dec_channels[-1], 4, kernel_size=1, stride=1, padding=0))
+    owner.decoder = nn.Sequential(*blocks)
+    owner.decoder_pos_embedding = SoftPositionEmbed(owner.slot_size, owner.dec_resolution)
+
+
+def broadcast_decode(owner, slots):
+    """slots [B, K, D] -> (recon_combined [B,3,H,W], recons [B,K,3,H,W], masks [B,K,1,H,W], slots).
+    Spatial broadcast, deconv stack, softmax over slots of the alpha channel (savi.py:504-525)."""
+    bs, num_slots, slot_size = slots.shape
+    H, W = owner.resolution
+    x = slots.reshape(bs * num_slots, slot_size, 1, 1).repeat(1, 1, *owner.dec_resolution)
+    x = owner.decoder(owner.decoder_pos_embedding(x)).view(bs, num_slots, 4, H, W)
+    recons, masks = x[:, :, :3], F.softmax(x[:, :, 3:], dim=1)
+    return (recons * masks).sum(dim=1), recons, masks, slots
+
+
+class StoSAVi(BaseModel):
+    """Slot Attention for Video with an (optionally stochastic) slot-initialisation head.
+    ``loss_dict['kld_method'] == 'none'`` gives plain deterministic SAVi."""
+
+    def __init__(self, resolution, clip_len,
+                 slot_dict=dict(num_slots=7, slot_size=128, slot_mlp_size=256, num_iterations=2,
+                                kernel_mlp=True),
+                 enc_dict=dict(enc_channels=(3, 64, 64, 64, 64), enc_ks=5, enc_out_channels=128,
+                               enc_norm=''),
+                 dec_dict=dict(dec_channels=(128, 64, 64, 64, 64), dec_resolution=(8, 8), dec_ks=5,
+                               dec_norm=''),
+                 pred_dict=dict(pred_type='transformer', pred_rnn=True, pred_norm_first=True,
+                                pred_num_layers=2, pred_num_heads=4, pred_ffn_dim=512,
+                                pred_sg_every=None),
+                 loss_dict=dict(use_post_recon_loss=True, kld_method='var-0.01'),
+                 eps=1e-6):
+        super().__init__()
+        self.resolution = resolution
+        self.clip_len = clip_len
+        self.eps = eps
+        self.slot_dict, self.enc_dict, self.dec_dict = slot_dict, enc_dict, dec_dict
+        self.pred_dict, self.loss_dict = pred_dict, loss_dict
+        self._build_slot_attention()
+        self._build_encoder()
+        self._build_decoder()
+        self._build_predictor()
+        self._build_loss()
+        self.testing = False        # True: forward returns slots only (offline extraction)
+
+    # ------------------------------------------------------------------ build
+    def _build_slot_attention(self):
+        sd = self.slot_dict
+        self.enc_out_channels = self.enc_dict['enc_out_channels']
+        self.num_slots, self.slot_size = sd['num_slots'], sd['slot_size']
+        self.slot_mlp_size, self.num_iterations = sd['slot_mlp_size'], sd['num_iterations']
+        D = self.slot_size
+        self.init_latents = nn.Parameter(nn.init.normal_(torch.empty(1, self.num_slots, D)))
+        if sd.get('kernel_mlp', True):
+            self.kernel_dist_layer = nn.Sequential(nn.Linear(D, 2 * D), nn.LayerNorm(2 * D),
+                                                   nn.ReLU(), nn.Linear(2 * D, 2 * D))
+        else:
+            self.kernel_dist_layer = nn.Sequential(nn.Linear(D, 2 * D))
+        # unused head kept so that released checkpoints load strictly
+        self.prior_slot_layer = nn.Sequential(nn.Linear(D, D), nn.LayerNorm(D), nn.ReLU(),
+                                              nn.Linear(D, D))
+        self.slot_attention = SlotAttention(in_features=self.enc_out_channels,
+                                            num_iterations=self.num_iterations,
+                                            num_slots=self.num_slots, slot_size=D,
+                                            mlp_hidden_size=self.slot_mlp_size, eps=self.eps)
+
+    def _build_encoder(self):
+        ed = self.enc_dict
+        self.enc_channels = list(ed['enc_channels'])
+        self.enc_ks, self.enc_norm = ed['enc_ks'], ed['enc_norm']
+        self.visual_resolution = (64, 64)       # the feature grid is 64x64 for 64^2 and 128^2 input
+        self.visual_channels = self.enc_channels[-1]
+        n = len(self.enc_channels) - 1
+        self.encoder = nn.Sequential(*[
+            conv_norm_act(self.enc_channels[i], self.enc_channels[i + 1], kernel_size=self.enc_ks,
+                          stride=2 if (i == 0 and self.resolution[0] == 128) else 1,
+                          norm=self.enc_norm, act='relu' if i != n - 1 else '')
+            for i in range(n)])
+        self.encoder_pos_embedding = SoftPositionEmbed(self.visual_channels,
+                                                       self.visual_resolution)
+        self.encoder_out_layer = nn.Sequential(
+            nn.LayerNorm(self.visual_channels),
+            nn.Linear(self.visual_channels, self.enc_out_channels), nn.ReLU(),
+            nn.Linear(self.enc_out_channels, self.enc_out_channels))
+
+    def _build_decoder(self):
+        build_broadcast_decoder(self)
+
+    def _build_predictor(self):
+        pd = self.pred_dict
+        if pd.get('pred_type', 'transformer') == 'mlp':
+            core = ResidualMLPPredictor([self.slot_size, self.slot_size * 2, self.slot_size],
+                                        norm_first=pd['pred_norm_first'])
+        else:
+            core = TransformerPredictor(self.slot_size, pd['pred_num_layers'],
+                                        pd['pred_num_heads'], pd['pred_ffn_dim'],
+                                        norm_first=pd['pred_norm_first'])
+        if pd['pred_rnn']:
+            core = RNNPredictorWrapper(core, self.slot_size, self.slot_mlp_size, num_layers=1,
+                                       rnn_cell='LSTM', sg_every=pd['pred_sg_every'])
+        self.predictor = core
+
+    def _build_loss(self):
+        self.use_post_recon_loss = self.loss_dict['use_post_recon_loss']
+        assert self.use_post_recon_loss
+        method = self.loss_dict['kld_method']
+        var = 1.0
+        if '-' in method:
+            method, v = method.split('-')
+            var = float(v)
+        self.kld_log_var = math.log(var)
+        self.kld_method = method
+        assert self.kld_method in ['var', 'none']
+
+    # ------------------------------------------------------------------ pieces
+    def _kld_loss(self, prior_dist, post_slots):
+        """KL( N(mu, sigma) || N(mu, kld_var) ): only the variance is penalised."""
+        if self.kld_method == 'none':
+            return torch.tensor(0.).type_as(prior_dist)
+        D = self.slot_size
+        assert prior_dist.shape[-1] == 2 * D
+        log_var1 = prior_dist[..., D:]
+        log_var2 = torch.full_like(log_var1, self.kld_log_var)
+        kld = 0.5 * (log_var2 - log_var1) + torch.exp(log_var1) / (2. * torch.exp(log_var2)) - 0.5
+        return kld.sum(-1).mean()
+
+    def _sample_dist(self, dist):
+        D = self.slot_size
+        assert dist.shape[-1] == 2 * D
+        mu = dist[..., :D]
+        if self.kld_method == 'none':
+            return mu
+        return mu + torch.randn_like(mu).detach() * torch.exp(0.5 * dist[..., D:])
+
+    def _get_encoder_out(self, img):
+        """img [N, 3, H, W] -> [N, 4096, enc_out_channels] feature vectors."""
+        x = self.encoder(img).type(self.dtype)
+        x = self.encoder_pos_embedding(x).flatten(2, 3).permute(0, 2, 1).contiguous()
+        return self.encoder_out_layer(x)
+
+    def encode(self, img, prev_slots=None):
+        """img [B, T, 3, H, W] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D], features)."""
+        B, T = img.shape[:2]
+        feats = self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
+        start = self.init_latents.repeat(B, 1, 1)
+        dists, slots = [], []
+        for t in range(T):                                  # frames are a serial chain
+            latents = start if prev_slots is None else self.predictor(prev_slots)
+            dist = self.kernel_dist_layer(latents)
+            prev_slots = self.slot_attention(feats[:, t], self._sample_dist(dist))   # hot path 1
+            dists.append(dist)
+            slots.append(prev_slots)
+        return torch.stack(dists, dim=1), torch.stack(slots, dim=1), feats
+
+    def _reset_rnn(self):
+        self.predictor.reset()
+
+    def decode(self, slots):
+        return broadcast_decode(self, slots)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, data_dict):
+        """Long evaluation videos are cut into temporal chunks (halving the chunk until it fits
+        in memory) with the slots carried across chunks."""
+        img = data_dict['img']
+        T = img.shape[1]
+        if T <= self.clip_len or self.training:
+            return self._forward(img, None)
+        clip_len = T
+        while True:
+            try:
+                probe = self._forward(img[:, :clip_len], None)
+                del probe
+                torch.cuda.empty_cache()
+                break
+            except RuntimeError:                            # CUDA out of memory
+                clip_len = clip_len // 2 + 1
+        self.clip_len = max(self.clip_len, clip_len)
+        if clip_len == T:
+            return self._forward(img, None)
+        pieces, prev_slots = None, None
+        for t0 in range(0, T, clip_len):
+            out = self._forward(img[:, t0:t0 + clip_len], prev_slots)
+            if pieces is None:
+                pieces = {k: [v.detach()] for k, v in out.items()}
+            else:
+                for k, v in out.items():
+                    pieces[k].append(v.detach())
+            prev_slots = pieces['post_slots'][-1][:, -1].detach().clone()
+            del out
+            torch.cuda.empty_cache()
+        return {k: torch_cat(v, dim=1) for k, v in pieces.items()}
+
+    def _forward(self, img, prev_slots=None):
+        if prev_slots is None:
+            self._reset_rnn()
+        B, T = img.shape[:2]
+        kernel_dist, post_slots, _ = self.encode(img, prev_slots=prev_slots)
+        out = {'post_slots': post_slots, 'kernel_dist': kernel_dist, 'img': img}
+        if self.testing:
+            return out
+        if self.use_post_recon_loss:
+            combined, recons, masks, _ = self.decode(post_slots.flatten(0, 1))
+            out.update(post_recon_combined=combined.unflatten(0, (B, T)),
+                       post_recons=recons.unflatten(0, (B, T)),
+                       post_masks=masks.unflatten(0, (B, T)))
+        return out
+
+    def calc_train_loss(self, data_dict, out_dict):
+        losses = {'kld_loss': self._kld_loss(out_dict['kernel_dist'], out_dict['post_slots'])}
+        if self.use_post_recon_loss:
+            losses['post_recon_loss'] = F.mse_loss(out_dict['post_recon_combined'],
+                                                   out_dict['img'])
+        return losses
+
+    @property
+    def dtype(self):
+        return self.slot_attention.dtype
+
+    @property
+    def device(self):
+        return self.slot_attention.device

@@ -1,0 +1,10 @@
+"""Task package surface of reference slotformer/video_prediction/__init__.py (build_model only)."""
+from .models import build_model  # noqa: F401
+
+
+def build_dataset(params, val_only=False):
+    raise NotImplementedError('datasets are out of scope of the sm_100a engine (SURVEY.md section 2, row 20)')
+
+
+def build_method(**kwargs):
+    raise NotImplementedError('the nerv trainer is out of scope of the sm_100a engine (SURVEY.md section 2, row 14)')

@@ -1,0 +1,138 @@
+"""Caller modules (SURVEY.md section 8 a9 / 8 b): StoSAVi and SlotFormer keep the reference's
+state_dict keys and reproduce the reference's outputs (tests/golden/wrappers.npz, produced by
+the UNMODIFIED reference loaded with our seeded state_dict)."""
+import glob
+import importlib.util
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import wrapper_cases as W
+from helpers import GOLD, rel_max
+
+REF = '/root/reference/slotformer'
+
+
+def _gold():
+    return np.load(os.path.join(GOLD, 'wrappers.npz'))
+
+
+def test_state_dict_keys_match_reference():
+    from slotformer_b200.base_slots.models import StoSAVi
+    from slotformer_b200.video_prediction.models import SlotFormer
+    g = _gold()
+    savi = W.build_savi(StoSAVi)
+    assert list(savi.state_dict().keys()) == g['savi_keys'].tolist()
+    with tempfile.TemporaryDirectory() as td:
+        ckpt = os.path.join(td, 'savi.pth')
+        torch.save({'state_dict': savi.state_dict()}, ckpt)
+        sf = W.build_slotformer(SlotFormer, ckpt)
+    assert list(sf.state_dict().keys()) == g['sf_keys'].tolist()
+    # the decoder was sliced out of the SAVi checkpoint by key prefix and is frozen
+    assert all(not p.requires_grad for p in sf.decoder.parameters())
+    assert torch.equal(sf.decoder[0][0].weight, savi.decoder[0][0].weight)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference config files only exist in the build container')
+def test_build_model_with_every_reference_config():
+    """params.py files of the reference load unchanged through the nerv shim and build."""
+    from slotformer_b200.compat import install_nerv_shim
+    from slotformer_b200 import base_slots, video_prediction
+    install_nerv_shim()
+
+    def load(path):
+        spec = importlib.util.spec_from_file_location('cfg_' + os.path.basename(path)[:-3].replace('-', '_'), path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.SlotFormerParams()
+
+    built = 0
+    with tempfile.TemporaryDirectory() as td:
+        ckpts = {}
+        for path in sorted(glob.glob(f'{REF}/base_slots/configs/*savi*_params*.py')):
+            params = load(path)
+            assert params.get('model') == 'StoSAVi' and params.get('no_such_key', 5) == 5
+            model = base_slots.build_model(params)
+            key = (tuple(params.resolution), params.slot_dict['slot_size'], tuple(params.dec_dict['dec_channels']),
+                   tuple(params.dec_dict['dec_resolution']))
+            ckpts[key] = os.path.join(td, f'savi{len(ckpts)}.pth')
+            torch.save({'state_dict': model.state_dict()}, ckpts[key])
+            built += 1
+        for path in sorted(glob.glob(f'{REF}/video_prediction/configs/slotformer_*_params*.py')):
+            params = load(path)
+            if params.model == 'STEVESlotFormer':
+                with pytest.raises(NotImplementedError):
+                    video_prediction.build_model(params)
+                continue
+            key = (tuple(params.resolution), params.slot_dict['slot_size'], tuple(params.dec_dict['dec_channels']),
+                   tuple(params.dec_dict['dec_resolution']))
+            assert key in ckpts, f'no SAVi decoder for {path}'
+            params.dec_dict['dec_ckp_path'] = ckpts[key]
+            model = video_prediction.build_model(params)
+            assert model.rollouter.history_len == params.rollout_dict['history_len']
+            built += 1
+    assert built >= 6
+
+
+@pytest.mark.gpu
+def test_stosavi_matches_reference_on_gpu():
+    from slotformer_b200.base_slots.models import StoSAVi
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = _gold()
+    m = W.build_savi(StoSAVi).cuda()
+    img = W.savi_input().cuda()
+    with torch.no_grad():
+        m.testing = True
+        out = m({'img': img})
+        assert set(out) == {'post_slots', 'kernel_dist', 'img'}
+        assert rel_max(out['post_slots'].cpu().numpy(), g['savi_post_slots']) < 2e-3
+        m.testing = False
+        full = m({'img': img})
+    assert rel_max(full['post_recon_combined'].cpu().numpy(), g['savi_recon']) < 2e-3
+    assert np.abs(full['post_masks'].cpu().numpy() - g['savi_masks']).max() < 2e-3
+    loss = m.calc_train_loss({'img': img}, full)
+    assert set(loss) == {'kld_loss', 'post_recon_loss'}
+
+
+@pytest.mark.gpu
+def test_slotformer_matches_reference_on_gpu():
+    from slotformer_b200.base_slots.models import StoSAVi
+    from slotformer_b200.video_prediction.models import SlotFormer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = _gold()
+    with tempfile.TemporaryDirectory() as td:
+        ckpt = os.path.join(td, 'savi.pth')
+        torch.save({'state_dict': W.build_savi(StoSAVi).state_dict()}, ckpt)
+        m = W.build_slotformer(SlotFormer, ckpt).cuda()
+    x = W.slotformer_input().cuda()
+    with torch.no_grad():
+        fwd = m({'slots': x})
+        assert rel_max(fwd['pred_slots'].cpu().numpy(), g['sf_pred']) < 4e-3
+        assert torch.equal(fwd['gt_slots'], x[:, 6:])
+        dec = m.rollout(x[:, :6], 3, decode=True, with_gt=False)
+        assert rel_max(dec['recon_combined'].cpu().numpy(), g['sf_recon']) < 4e-3
+        loss = m.calc_train_loss({'slots': x}, fwd)
+    assert abs(loss['slot_recon_loss'].item() - float(g['sf_loss'])) < 1e-2 * float(g['sf_loss'])
+    m.rollout_len = 2          # mutable at run time, as the offline rollout scripts do
+    with torch.no_grad():
+        assert m({'slots': x[:, :8]})['pred_slots'].shape == (2, 2, 5, 128)
+
+
+@pytest.mark.gpu
+def test_training_step_uses_autograd_path():
+    """Gradients flow through both operators (differentiable restatement, GPU eager)."""
+    from slotformer_b200.base_slots.models import SlotAttention
+    from slotformer_b200.video_prediction.models import SlotRollouter
+    sa = SlotAttention(128, 2, 4, 128, 256).cuda().train()
+    out = sa(torch.randn(2, 256, 128, device='cuda'), torch.randn(2, 4, 128, device='cuda'))
+    out.square().mean().backward()
+    assert sa.project_k.weight.grad is not None and torch.isfinite(sa.project_k.weight.grad).all()
+    ro = SlotRollouter(3, 128, 2, num_layers=2).cuda().eval()
+    x = torch.randn(2, 2, 3, 128, device='cuda', requires_grad=True)
+    ro(x, 2).square().mean().backward()
+    assert x.grad is not None and ro.in_proj.weight.grad is not None
