@@ -44,8 +44,8 @@ WORKLOAD = ('OBJ3D SlotFormer rollout, B=64, 128x128 (64x64 feature grid), K=6, 
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the kernels of ONE sfb_sa_forward call on this
 # workload, from the ncu --set full capture summarised in profiles/ (None until captured)
-SA_TRAFFIC_BYTES = None
-SA_TRAFFIC_SOURCE = None
+SA_TRAFFIC_BYTES = 1581e6
+SA_TRAFFIC_SOURCE = 'profiles/r1_bench_launch_list.txt (ncu dram__bytes_read+write over the 5 SA launches of one step)'
 
 
 def sa_bytes_per_frame():

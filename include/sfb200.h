@@ -90,7 +90,13 @@ typedef struct sfb_sa_weights {
  * per-(frame, pixel-chunk) partial sums and the fp16 x^ ring of one frame chunk. */
 size_t sfb_sa_workspace_bytes(int B, int N, int C, int D, int Dm, int n_iter, int chunk_frames);
 
-/* Slot Attention forward for B independent frames.
+/* Fold the projections (W_qk = scale*log2e*gamma*(Wq^T Wk)^T, W_iv = W_ih Wv, logit-bias vector) and
+ * pack all slot-update weights as swizzled fp16 hi/lo panels into the head of `workspace`.  Call
+ * again whenever a weight tensor changed or the workspace moved; sfb_sa_forward only reads it. */
+int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Slot Attention forward for B independent frames (after sfb_sa_prepare on the same workspace).
  *   feats        [B, N, C]  fp32 (feat_dtype = SFB_DTYPE_F32); rows contiguous, frame b at
  *                feats + b*feat_batch_stride elements (savi.py:406 passes encoder_out[:, idx])
  *   slots_in     [B, K, D]  fp32 initial slots          slots_out [B, K, D] fp32

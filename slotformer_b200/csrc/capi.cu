@@ -105,6 +105,27 @@ size_t sfb_sa_workspace_bytes(int B, int N, int C, int D, int Dm, int n_iter, in
     return ws.total;
 }
 
+int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    if (!w || !workspace) return SFB_E_NULL;
+    const float* const* wp = reinterpret_cast<const float* const*>(w);
+    for (size_t i = 0; i < sizeof(sfb_sa_weights) / sizeof(const float*); ++i)
+        if (!wp[i]) return SFB_E_NULL;
+    if (!sfb::sa_shape_supported(C, D, Dm)) return SFB_E_BAD_SHAPE;
+    if (!aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    sfb::SAWorkspace ws;
+    sfb::sa_workspace_layout(1, 1, 16, C, D, Dm, 1, &ws);      // the weight regions come first
+    if (workspace_bytes < ws.qt) return SFB_E_WORKSPACE;
+    cudaError_t e = sfb::sa_prep_launch(w->project_q_1_weight, w->project_k_weight, w->project_v_weight,
+                                        w->gru_weight_ih, w->gru_weight_hh, w->mlp_1_weight, w->mlp_3_weight,
+                                        w->norm_inputs_weight, w->norm_inputs_bias,
+                                        reinterpret_cast<char*>(workspace), ws, C, D, Dm,
+                                        reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(2);
+    return SFB_OK;
+}
+
 int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const float* slots_in, float* slots_out, float* seg_mask,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
@@ -132,13 +153,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);
     char* base = reinterpret_cast<char*>(workspace);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-
-    cudaError_t e = sfb::sa_prep_launch(w->project_q_1_weight, w->project_k_weight, w->project_v_weight,
-                                        w->gru_weight_ih, w->gru_weight_hh, w->mlp_1_weight,
-                                        w->mlp_3_weight, w->norm_inputs_weight, w->norm_inputs_bias, base, ws,
-                                        C, D, Dm, st);
-    if (e != cudaSuccess) return cuda_err(e);
-    g_launches.fetch_add(1);
+    cudaError_t e;
 
     auto H = [&](size_t off) { return reinterpret_cast<const __half*>(base + off); };
     sfb::SAUpdateParams up{};

@@ -49,7 +49,7 @@ struct Producer {
     uint64_t pol;
     __device__ __forceinline__ void emit(const GemmOp& op, int nb, int kb) {
         const int s = pidx % ring.nstage;
-        mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+        mbar_wait_sleep(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
         mbar_arrive_expect_tx(&ring.full[s], RO_PANEL_BYTES);
         bulk_g2s(ring.stages + (size_t)s * RO_PANEL_BYTES,
                  op.base + (((size_t)((op.nb0 + nb) >> 1) * op.kpt + op.kb0 + kb) * 2 + ((op.nb0 + nb) & 1)) * RO_PANEL_HALVES,

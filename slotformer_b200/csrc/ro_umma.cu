@@ -21,7 +21,9 @@
 
 namespace sfb {
 
-static constexpr int RU_TILE_BYTES = 16384;
+static constexpr int RU_TILE_BYTES = 16384;                 // one 128 x 64 weight tile
+static constexpr int RU_STAGE_TILES = 2;                    // k-adjacent tiles per ring stage
+static constexpr int RU_STAGE_BYTES = RU_STAGE_TILES * RU_TILE_BYTES;
 static constexpr int RU_TILE_HALVES = 8192;
 static constexpr int RU_SYNC_THREADS = RO_THREADS + 32;   // compute warps + MMA warp
 static constexpr int RU_THREADS = RO_THREADS + 64;
@@ -49,14 +51,15 @@ struct BProducer {
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) {
         for (int t = 0; t < op.ntile; ++t)
-            for (int kb = 0; kb < op.nkb; ++kb, ++pidx) {
+            for (int kb = 0; kb < op.nkb; kb += RU_STAGE_TILES, ++pidx) {
+                const int nk = (op.nkb - kb) < RU_STAGE_TILES ? (op.nkb - kb) : RU_STAGE_TILES;
                 const int s = pidx % ring.nstage;
-                mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+                mbar_wait_sleep(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
                 if (dbg & 1) { mbar_arrive(&ring.full[s]); continue; }
-                mbar_arrive_expect_tx(&ring.full[s], RU_TILE_BYTES);
-                bulk_g2s(ring.stages + (size_t)s * RU_TILE_BYTES,
+                mbar_arrive_expect_tx(&ring.full[s], nk * RU_TILE_BYTES);
+                bulk_g2s(ring.stages + (size_t)s * RU_STAGE_BYTES,
                          op.base + ((size_t)(op.tile0 + t) * op.kpt + op.kb0 + kb) * RU_TILE_HALVES,
-                         RU_TILE_BYTES, &ring.full[s], pol);
+                         nk * RU_TILE_BYTES, &ring.full[s], pol);
             }
     }
     __device__ __forceinline__ void sync() {}
@@ -76,17 +79,21 @@ struct BMma {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(128, ntok);
             for (int t = 0; t < op.ntile; ++t)
-                for (int kb = 0; kb < op.nkb; ++kb, ++pidx) {
+                for (int kb = 0; kb < op.nkb; kb += RU_STAGE_TILES, ++pidx) {
+                    const int nk = (op.nkb - kb) < RU_STAGE_TILES ? (op.nkb - kb) : RU_STAGE_TILES;
                     const int s = pidx % ring.nstage;
-                    mbar_wait(&ring.full[s], (pidx / ring.nstage) & 1);
+                    mbar_wait_sleep(&ring.full[s], (pidx / ring.nstage) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_u32 = smem_u32(ring.stages + (size_t)s * RU_TILE_BYTES);
+                    const uint32_t a_u32 = smem_u32(ring.stages + (size_t)s * RU_STAGE_BYTES);
                     if (!(dbg & 2))
+                        for (int kk = 0; kk < nk; ++kk)
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        umma_f16(tmem + (uint32_t)(t * ntok), umma_smem_desc(a_u32 + k4 * 32),
-                                 umma_smem_desc(b_u32 + kb * kblock_bytes + k4 * 32), idesc, (kb | k4) != 0);
-                    umma_commit(&ring.empty[s]);      // stage is free once these MMAs have read it
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_f16(tmem + (uint32_t)(t * ntok), umma_smem_desc(a_u32 + kk * RU_TILE_BYTES + k4 * 32),
+                                         umma_smem_desc(b_u32 + (kb + kk) * kblock_bytes + k4 * 32), idesc,
+                                         (kb | kk | k4) != 0);
+                    if (dbg & 8) mbar_arrive(&ring.empty[s]);   // (timing experiment only: frees the stage early)
+                    else umma_commit(&ring.empty[s]);           // stage is free once these MMAs have read it
                 }
             umma_commit(accfull);                     // accumulators of this GEMM are complete
         }
@@ -130,7 +137,7 @@ struct BCompute {
         tcgen05_fence_before();
     }
     __device__ __forceinline__ void sync() {
-        fence_proxy_async();            // operand tiles written by these threads -> tensor-core reads
+        if (!(dbg & 16)) fence_proxy_async();   // operand tiles written by these threads -> tensor-core reads
         named_bar_sync(1, RU_SYNC_THREADS);
     }
 };
@@ -223,7 +230,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 const float* l2b = l1w + 3 * DMODEL;
                 if (Role::kCompute) {
                     if (p.par_double) load_params((layer + 1) % p.layers, (lcount + 1) & 1);
-                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
+                    if (!(p.dbg & 64)) ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
                 }
                 R.sync();
                 stamp();   // LN1
@@ -242,7 +249,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 }
                 R.sync();
                 stamp();   // qkv
-                if (Role::kCompute) {
+                if (Role::kCompute && !(p.dbg & 32)) {
                     if (NKB <= 6) {
                         for (int hh = warp; hh < p.heads; hh += RO_WARPS)
                             attn_head<DH, (NKB <= 6 ? NKB : 2), (NKB <= 6 ? NKB / 2 : 1)>(
@@ -270,7 +277,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 }
                 R.sync();
                 stamp();   // outproj
-                if (Role::kCompute)
+                if (Role::kCompute && !(p.dbg & 64))
                     ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l2w, l2b, warp, lane);
                 R.sync();
                 stamp();   // LN2
@@ -405,13 +412,13 @@ int ro_umma_plan(ROParams* p, int smem_limit, size_t* smem_bytes) {
         p->off_par = (uint32_t)off; off += par_bytes;
         p->off_bars = (uint32_t)off; off += 20 * 8;
         off = (off + 1023) / 1024 * 1024;
-        if ((size_t)smem_limit < off + 3 * (size_t)RU_TILE_BYTES) continue;
-        int nstage = (int)(((size_t)smem_limit - off) / RU_TILE_BYTES);
-        if (nstage > 8) nstage = 8;
+        if ((size_t)smem_limit < off + 2 * (size_t)RU_STAGE_BYTES) continue;
+        int nstage = (int)(((size_t)smem_limit - off) / RU_STAGE_BYTES);
+        if (nstage > 6) nstage = 6;
         p->off_ring = (uint32_t)off;
         p->nstage = nstage; p->par_double = par_double; p->hg = p->heads; p->fc = fc;
         p->lda = 0; p->ldb = 0;
-        *smem_bytes = off + (size_t)nstage * RU_TILE_BYTES;
+        *smem_bytes = off + (size_t)nstage * RU_STAGE_BYTES;
         return 0;
     }
     return -1;

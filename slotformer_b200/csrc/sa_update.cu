@@ -99,7 +99,7 @@ struct UProducer {
                                          const __half*, int, Acc&) {
         for (int kb = 0; kb < nkb; ++kb, ++pidx) {
             const int s = pidx % ring.nstage;
-            mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+            mbar_wait_sleep(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
             mbar_arrive_expect_tx(&ring.full[s], PAIR_BYTES);
             bulk_g2s(ring.stages + (size_t)s * PAIR_BYTES, base + ((size_t)nb * kpt + kb) * PAIR_HALVES,
                      PAIR_BYTES, &ring.full[s], pol);

@@ -74,6 +74,9 @@ def load():
                                         c.c_void_p, c.c_size_t, c.c_void_p]
     lib.sfb_sa_workspace_bytes.restype = c.c_size_t
     lib.sfb_sa_workspace_bytes.argtypes = [c.c_int] * 7
+    lib.sfb_sa_prepare.restype = c.c_int
+    lib.sfb_sa_prepare.argtypes = [c.POINTER(_SAWeights), c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t,
+                                   c.c_void_p]
     lib.sfb_sa_forward.restype = c.c_int
     lib.sfb_sa_forward.argtypes = [
         c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p,
@@ -96,7 +99,7 @@ def load():
 def exported_symbols():
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
     return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_debug_set_profile',
-            'sfb_debug_umma_gemm', 'sfb_sa_workspace_bytes',
+            'sfb_debug_umma_gemm', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
             'sfb_rollout_forward']
 
@@ -148,6 +151,7 @@ class SlotAttentionEngine:
 
     def __init__(self):
         self._ws = None
+        self._key = None
 
     def forward(self, feats, slots, weights, num_iterations, eps, mlp_hidden_size,
                 return_mask=False, chunk_frames=0):
@@ -177,6 +181,7 @@ class SlotAttentionEngine:
             raise SfbError(f'unsupported Slot Attention shape B={B} N={N} C={C} D={D}')
         if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            self._key = None
         wt = []
         cw = _SAWeights()
         for k in SA_WEIGHT_KEYS:
@@ -188,6 +193,11 @@ class SlotAttentionEngine:
         out = torch.empty((B, K, D), dtype=torch.float32, device=dev)
         mask = torch.empty((B, K, N), dtype=torch.float32, device=dev) if return_mask else None
         with torch.cuda.device(dev):
+            key = _weights_key(wt)
+            if key != self._key:       # weights changed (or first call): fold + pack once
+                _check(lib.sfb_sa_prepare(ctypes.byref(cw), C, D, int(mlp_hidden_size), self._ws.data_ptr(),
+                                          self._ws.numel(), _stream(dev)))
+                self._key = key
             rc = lib.sfb_sa_forward(
                 feats.data_ptr(), SFB_DTYPE_F32, bstride, slots.data_ptr(), out.data_ptr(),
                 mask.data_ptr() if return_mask else None, ctypes.byref(cw), B, N, C, D,

@@ -73,6 +73,16 @@ class SlotRollouter(Rollouter):
     # -- helpers ---------------------------------------------------------- #
     def _token_pe(self):
         """[T*K, d] positional row per window token (time-major, slot-minor)."""
+        srcs = [self.enc_t_pe] + ([self.enc_slots_pe] if self.enc_slots_pe is not None else [])
+        key = tuple((t.data_ptr(), t._version, t.requires_grad and torch.is_grad_enabled()) for t in srcs)
+        if getattr(self, '_pe_key', None) == key:
+            return self._pe_cache
+        pe = self._token_pe_uncached()
+        if not any(k[2] for k in key):
+            self._pe_key, self._pe_cache = key, pe
+        return pe
+
+    def _token_pe_uncached(self):
         T = self.enc_t_pe.shape[1]
         pe = self.enc_t_pe[0].unsqueeze(1).expand(T, self.num_slots, -1)
         if self.enc_slots_pe is not None:
