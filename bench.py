@@ -135,8 +135,18 @@ def cpu_threads():
     return os.cpu_count() or 1
 
 
+def _all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is allowed every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def cpu_sample_step(sa_w, ro_w, pe, clips):
     """One bounded sample of the workload on the host: `clips` clips (clips*T_in frames)."""
+    _all_cores()
     from oracle import slot_oracle as O
     import cases
     feats, slots = cases.make_sa_inputs(clips * WL['T_in'], WL['N'], WL['C'], WL['D'], WL['K'], seed=1)

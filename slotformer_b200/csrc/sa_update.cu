@@ -176,7 +176,7 @@ __device__ __forceinline__ void ln_rows_split(const float* src, int lds, __half*
     constexpr int PER = D / 32;
     float gm[PER], bt[PER];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { gm[i] = __ldg(gw + lane + 32 * i); bt[i] = __ldg(gb + lane + 32 * i); }
+    for (int i = 0; i < PER; ++i) { gm[i] = gw[lane + 32 * i]; bt[i] = gb[lane + 32 * i]; }
     for (int r = warp; r < rows; r += UPD_WARPS) {
         float v[PER];
         float s = 0.f;
@@ -204,7 +204,10 @@ struct UpdCfg {
     static constexpr int OFF_A = 0;                                  // a_hi | a_lo
     static constexpr int OFF_H = OFF_A + 2 * ROWS * LDA * 2;         // h_hi | h_lo (also previous slots)
     static constexpr int OFF_SP = OFF_H + 2 * ROWS * LDH * 2;        // fp32 state
-    static constexpr int OFF_BARS = OFF_SP + ROWS * LDS * 4;
+    // staged parameters: b_ih[3D] b_hh[3D] b1[DM] b2[D] ln_m_w/b[2D] ln_q_w/b[2D] ln_in_w/b[2C] wbeta[D]
+    static constexpr int PAR_FLOATS = 6 * D + DM + D + 2 * D + 2 * D + 2 * C + D;
+    static constexpr int OFF_PAR = OFF_SP + ROWS * LDS * 4;
+    static constexpr int OFF_BARS = OFF_PAR + PAR_FLOATS * 4;
     static constexpr int OFF_RING = (OFF_BARS + 2 * 8 * 8 + 1023) / 1024 * 1024;
     static constexpr int NST_FIT = (232448 - OFF_RING) / PAIR_BYTES;
     static constexpr int NST = NST_FIT > 8 ? 8 : NST_FIT;
@@ -222,6 +225,18 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
     __half* h_hi = reinterpret_cast<__half*>(smem + Cfg::OFF_H);
     __half* h_lo = h_hi + ROWS * LDH;
     float* sp = reinterpret_cast<float*>(smem + Cfg::OFF_SP);
+    const float* par = reinterpret_cast<const float*>(smem + Cfg::OFF_PAR);
+    const float* s_bih = par;
+    const float* s_bhh = par + 3 * D;
+    const float* s_b1 = par + 6 * D;
+    const float* s_b2 = s_b1 + DM;
+    const float* s_lnm_w = s_b2 + D;
+    const float* s_lnm_b = s_lnm_w + D;
+    const float* s_lnq_w = s_lnm_b + D;
+    const float* s_lnq_b = s_lnq_w + D;
+    const float* s_lnin_w = s_lnq_b + D;
+    const float* s_lnin_b = s_lnin_w + C;
+    const float* s_wbeta = s_lnin_b + C;
     const SAWeightsDev& w = p.w;
     const int K = p.K, N = p.N;
     const int g = lane >> 2, t4 = lane & 3;
@@ -232,44 +247,58 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
     if (p.do_update) {
         if (Role::kConsumer) {
             // ---- u^ = (sum_chunks U / 1024 + eps*xsum) / (sum_chunks colsum / 1024 + N*eps) ----
+            // (all partial-sum loads of a row are issued before the first use: one L2 latency per row)
             for (int r = warp; r < ROWS; r += UPD_WARPS) {
                 const int f = fbase + (r >> 3), slot = r & 7;
                 const bool ok = row_ok(r);
-                float den = 1.f, csn = 0.f;
+                float us[C / 32], xs[C / 32], sprev[C / 32], cs = 0.f;
+#pragma unroll
+                for (int i = 0; i < C / 32; ++i) { us[i] = 0.f; xs[i] = 0.f; sprev[i] = 0.f; }
                 if (ok) {
-                    float cs = 0.f;
-                    for (int ch = 0; ch < p.nchunk; ++ch)
-                        cs += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + 8 * C + slot);
-                    csn = cs * (1.f / SA_PSCALE);
-                    den = csn + (float)N * p.eps;
+                    const float* pbase = p.partials + (size_t)f * p.nchunk * p.pstride;
+#pragma unroll
+                    for (int i = 0; i < C / 32; ++i)
+                        sprev[i] = __ldg(p.slots_prev + ((size_t)f * K + slot) * D + lane + 32 * i);
+                    for (int ch0 = 0; ch0 < p.nchunk; ch0 += 4) {
+                        float tu[4][C / 32], tx[4][C / 32], tc[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bool in = (ch0 + q) < p.nchunk;
+                            const float* pq = pbase + (size_t)(in ? ch0 + q : ch0) * p.pstride;
+                            tc[q] = in ? __ldg(pq + 8 * C + slot) : 0.f;
+#pragma unroll
+                            for (int i = 0; i < C / 32; ++i) {
+                                tu[q][i] = in ? __ldg(pq + slot * C + lane + 32 * i) : 0.f;
+                                tx[q][i] = (in && p.first) ? __ldg(pq + 8 * C + 8 + lane + 32 * i) : 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            cs += tc[q];
+#pragma unroll
+                            for (int i = 0; i < C / 32; ++i) { us[i] += tu[q][i]; xs[i] += tx[q][i]; }
+                        }
+                    }
                 }
+                const float csn = cs * (1.f / SA_PSCALE);
+                const float den = ok ? csn + (float)N * p.eps : 1.f;
 #pragma unroll
                 for (int i = 0; i < C / 32; ++i) {
                     const int c = lane + 32 * i;
-                    float u = 0.f, sprev = 0.f;
+                    float u = 0.f;
                     if (ok) {
-                        float us = 0.f;
-                        for (int ch = 0; ch < p.nchunk; ++ch)
-                            us += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + slot * C + c);
-                        float xsv;
-                        if (p.first) {
-                            xsv = 0.f;
-                            for (int ch = 0; ch < p.nchunk; ++ch)
-                                xsv += __ldg(p.partials + ((size_t)f * p.nchunk + ch) * p.pstride + 8 * C + 8 + c);
-                            if (slot == 0) p.xsum[(size_t)f * C + c] = xsv;
-                        } else {
-                            xsv = p.xsum[(size_t)f * C + c];
-                        }
+                        float xsv = xs[i];
+                        if (p.first) { if (slot == 0) p.xsum[(size_t)f * C + c] = xsv; }
+                        else xsv = p.xsum[(size_t)f * C + c];
                         // t-statistics -> x^ statistics: x^ = gamma*t + beta
-                        const float gmc = __ldg(w.ln_in_w + c), btc = __ldg(w.ln_in_b + c);
+                        const float gmc = s_lnin_w[c], btc = s_lnin_b[c];
                         const float xs_hat = fmaf(gmc, xsv, (float)N * btc);
-                        const float us_hat = fmaf(gmc, us * (1.f / SA_PSCALE), btc * csn);
+                        const float us_hat = fmaf(gmc, us[i] * (1.f / SA_PSCALE), btc * csn);
                         u = (us_hat + p.eps * xs_hat) / den;
-                        sprev = __ldg(p.slots_prev + ((size_t)f * K + slot) * D + c);
                     }
                     store_split(a_hi, a_lo, r * LDA + c, u);
-                    store_split(h_hi, h_lo, r * LDH + c, sprev);     // previous slots as GEMM operand
-                    sp[r * LDS + c] = sprev;
+                    store_split(h_hi, h_lo, r * LDH + c, sprev[i]);     // previous slots as GEMM operand
+                    sp[r * LDS + c] = sprev[i];
                 }
             }
             R.sync();
@@ -292,9 +321,9 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
                 float bir[2], bhr[2], biz[2], bhz[2], bin_[2], bhn[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    bir[q] = __ldg(w.b_ih + col0 + q); bhr[q] = __ldg(w.b_hh + col0 + q);
-                    biz[q] = __ldg(w.b_ih + D + col0 + q); bhz[q] = __ldg(w.b_hh + D + col0 + q);
-                    bin_[q] = __ldg(w.b_ih + 2 * D + col0 + q); bhn[q] = __ldg(w.b_hh + 2 * D + col0 + q);
+                    bir[q] = s_bih[col0 + q]; bhr[q] = s_bhh[col0 + q];
+                    biz[q] = s_bih[D + col0 + q]; bhz[q] = s_bhh[D + col0 + q];
+                    bin_[q] = s_bih[2 * D + col0 + q]; bhn[q] = s_bhh[2 * D + col0 + q];
                 }
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb)
@@ -311,7 +340,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
         }
         if (Role::kConsumer) {
             R.sync();
-            ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, w.ln_m_w, w.ln_m_b, warp, lane);
+            ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, s_lnm_w, s_lnm_b, warp, lane);
             R.sync();
         }
         // ---- MLP hidden: h = relu(LN(s') W1^T + b1) ----
@@ -322,7 +351,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
             R.gemm(w.w1, D / 64, nb, D / 64, a_hi, a_lo, LDA, acc);
             if (Role::kConsumer) {
                 const int col0 = 64 * nb + 8 * warp + 2 * t4;
-                const float b0 = __ldg(w.b1 + col0), b1v = __ldg(w.b1 + col0 + 1);
+                const float b0 = s_b1[col0], b1v = s_b1[col0 + 1];
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb)
 #pragma unroll
@@ -342,7 +371,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
             R.gemm(w.w2, DM / 64, nb, DM / 64, h_hi, h_lo, LDH, acc);
             if (Role::kConsumer) {
                 const int col0 = 64 * nb + 8 * warp + 2 * t4;
-                const float b0 = __ldg(w.b2 + col0), b1v = __ldg(w.b2 + col0 + 1);
+                const float b0 = s_b2[col0], b1v = s_b2[col0 + 1];
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb)
 #pragma unroll
@@ -371,7 +400,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
     if (p.do_q) {
         // ---- q~ = LNq(S) W_qk^T -> fp16 hi/lo, rows >= K are zero ----
         if (Role::kConsumer) {
-            ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, w.ln_q_w, w.ln_q_b, warp, lane);
+            ln_rows_split<D>(sp, LDS, a_hi, a_lo, LDA, ROWS, s_lnq_w, s_lnq_b, warp, lane);
             __syncwarp();
             // per-slot logit bias  beta . q~[m]  =  LNq(S)[m] . wbeta   (rows of this warp)
             for (int r = warp; r < ROWS; r += UPD_WARPS) {
@@ -379,7 +408,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
 #pragma unroll
                 for (int i = 0; i < D / 32; ++i) {
                     const int e = lane + 32 * i;
-                    a = fmaf(__half2float(a_hi[r * LDA + e]) + __half2float(a_lo[r * LDA + e]), __ldg(w.wbeta + e), a);
+                    a = fmaf(__half2float(a_hi[r * LDA + e]) + __half2float(a_lo[r * LDA + e]), s_wbeta[e], a);
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -425,6 +454,18 @@ __global__ void __launch_bounds__(UPD_THREADS + 32, 1) sa_update_kernel(const SA
     if (tid == 0) {
         for (int s = 0; s < Cfg::NST; ++s) { mbar_init(&ring.full[s], 1); mbar_init(&ring.empty[s], UPD_WARPS); }
         fence_mbar_init();
+    }
+    {
+        constexpr int D = Cfg::D, DM = Cfg::DM;
+        float* par = reinterpret_cast<float*>(smem + Cfg::OFF_PAR);
+        const float* srcs[11] = {p.w.b_ih, p.w.b_hh, p.w.b1, p.w.b2, p.w.ln_m_w, p.w.ln_m_b, p.w.ln_q_w, p.w.ln_q_b,
+                                 p.w.ln_in_w, p.w.ln_in_b, p.w.wbeta};
+        const int lens[11] = {3 * D, 3 * D, DM, D, D, D, D, D, C, C, D};
+        int off = 0;
+        for (int sgm = 0; sgm < 11; ++sgm) {
+            for (int i = tid; i < lens[sgm]; i += UPD_THREADS + 32) par[off + i] = __ldg(srcs[sgm] + i);
+            off += lens[sgm];
+        }
     }
     __syncthreads();
     if (warp == UPD_WARPS) {
