@@ -84,14 +84,23 @@ struct BMma {
                     const int s = pidx % ring.nstage;
                     mbar_wait_sleep(&ring.full[s], (pidx / ring.nstage) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_u32 = smem_u32(ring.stages + (size_t)s * RU_STAGE_BYTES);
-                    if (!(dbg & 2))
-                        for (int kk = 0; kk < nk; ++kk)
+                    // descriptors are built once per stage; a K step of 16 (32 B) or the next k tile only
+                    // advances the 16-byte-granular start-address field
+                    const uint64_t da0 = umma_smem_desc(smem_u32(ring.stages + (size_t)s * RU_STAGE_BYTES));
+                    const uint64_t db0 = umma_smem_desc(b_u32 + kb * kblock_bytes);
+                    const uint32_t dtm = tmem + (uint32_t)(t * ntok);
+                    if (!(dbg & 2)) {
 #pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4)
-                                umma_f16(tmem + (uint32_t)(t * ntok), umma_smem_desc(a_u32 + kk * RU_TILE_BYTES + k4 * 32),
-                                         umma_smem_desc(b_u32 + (kb + kk) * kblock_bytes + k4 * 32), idesc,
-                                         (kb | kk | k4) != 0);
+                        for (int kk = 0; kk < RU_STAGE_TILES; ++kk) {
+                            if (kk < nk) {
+                                const uint64_t dbk = db0 + (uint64_t)((kk * kblock_bytes) >> 4);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    umma_f16(dtm, da0 + (uint64_t)((kk * RU_TILE_BYTES + k4 * 32) >> 4),
+                                             dbk + (uint64_t)((k4 * 32) >> 4), idesc, (kb | kk | k4) != 0);
+                            }
+                        }
+                    }
                     if (dbg & 8) mbar_arrive(&ring.empty[s]);   // (timing experiment only: frees the stage early)
                     else umma_commit(&ring.empty[s]);           // stage is free once these MMAs have read it
                 }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
     __syncthreads();
     if (my_items == 0) return;
 
-    const uint64_t pol = FIRST ? l2_policy_evict_first() : l2_policy_evict_last();
+    const uint64_t pol = (FIRST || (p.dbg & 8)) ? l2_policy_evict_first() : l2_policy_evict_last();
 
     auto issue = [&](uint32_t n) {
         if (n < total_tiles && lane == 0) {
