@@ -97,7 +97,7 @@ int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspac
                    void* stream);
 
 /* Slot Attention forward for B independent frames (after sfb_sa_prepare on the same workspace).
- *   feats        [B, N, C]  fp32 (feat_dtype = SFB_DTYPE_F32); rows contiguous, frame b at
+ *   feats        [B, N, C]  fp32 (SFB_DTYPE_F32) or bf16 (SFB_DTYPE_BF16); rows contiguous, frame b at
  *                feats + b*feat_batch_stride elements (savi.py:406 passes encoder_out[:, idx])
  *   slots_in     [B, K, D]  fp32 initial slots          slots_out [B, K, D] fp32
  *   seg_mask     NULL, or [B, K, N] fp32: softmax-over-slots attention of the LAST iteration,

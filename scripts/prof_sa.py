@@ -20,6 +20,8 @@ def timed(fn, n=5):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3
 with torch.no_grad():
+    if os.environ.get('BF16'):
+        feats = feats.to(torch.bfloat16)
     for chunk in [int(x) for x in os.environ.get('CHUNKS', '0,384').split(',')]:
         sa.chunk_frames = chunk
         for it in (1, 2):

@@ -75,7 +75,8 @@ class SlotAttention(nn.Module):
         if self._needs_autograd(inputs, slots):
             return self._autograd_forward(inputs, slots, return_mask)
         return self._engine.forward(
-            inputs.detach().float(), slots.detach().float(),
+            inputs.detach() if inputs.dtype == torch.bfloat16 else inputs.detach().float(),
+            slots.detach().float(),
             {k: v.detach() for k, v in self._weights().items()},
             self.num_iterations, self.eps, self.mlp_hidden_size, return_mask=return_mask,
             chunk_frames=self.chunk_frames)

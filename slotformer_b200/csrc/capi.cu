@@ -137,9 +137,9 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     for (size_t i = 0; i < sizeof(sfb_sa_weights) / sizeof(const float*); ++i)
         if (!wp[i]) return SFB_E_NULL;
     if (B < 0 || N < 1 || K < 1 || K > 8 || n_iter < 1) return SFB_E_BAD_SHAPE;
-    if (feat_dtype != SFB_DTYPE_F32) return SFB_E_BAD_SHAPE;
+    if (feat_dtype != SFB_DTYPE_F32 && feat_dtype != SFB_DTYPE_BF16) return SFB_E_BAD_SHAPE;
     if (!sfb::sa_shape_supported(C, D, Dm)) return SFB_E_BAD_SHAPE;
-    if (feat_batch_stride < (int64_t)N * C || (feat_batch_stride & 3)) return SFB_E_BAD_ALIGN;
+    if (feat_batch_stride < (int64_t)N * C || (feat_batch_stride & 7)) return SFB_E_BAD_ALIGN;
     if (!aligned16(feats) || !aligned16(slots_in) || !aligned16(slots_out) || !aligned16(workspace))
         return SFB_E_BAD_ALIGN;
     if (workspace_bytes < sfb_sa_workspace_bytes(B, N, C, D, Dm, n_iter, chunk_frames)) return SFB_E_WORKSPACE;
@@ -171,7 +171,8 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     up.B = B; up.N = N; up.K = K; up.nchunk = ws.nchunk; up.pstride = ws.pstride; up.eps = eps;
 
     sfb::SAPassParams pp{};
-    pp.feats = reinterpret_cast<const float*>(feats);
+    pp.feats = feats;
+    pp.feat_esize = (feat_dtype == SFB_DTYPE_BF16) ? 2 : 4;
     pp.feat_bstride = feat_batch_stride;
     pp.qt = up.qt;
     pp.partials = reinterpret_cast<float*>(base + ws.partials);

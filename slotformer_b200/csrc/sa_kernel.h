@@ -35,7 +35,8 @@ struct SAWorkspace {
 };
 
 struct SAPassParams {
-    const float* feats;
+    const void* feats;         // fp32 or bf16 (feat_esize bytes per element)
+    int feat_esize;
     long long feat_bstride;    // elements between frames
     __half* xhat;              // nullable when there is no later pass
     const __half* qt;          // per frame: hi [8][C], lo [8][C], 8 fp32 logit biases

@@ -26,8 +26,9 @@
 
 namespace sfb {
 
-static constexpr int PASS_WARPS = 8;
-static constexpr int PASS_THREADS = PASS_WARPS * 32;
+// warps per CTA.  12 warps (3 per scheduler, 2-stage rings) were measured SLOWER than 8 warps with
+// 3-stage rings (481 vs 433 us per Slot Attention call): ring depth matters more than warp count.
+constexpr int pass_warps(int C) { return C == 128 ? 8 : 8; }
 static constexpr float SA_PSCALE = 1024.f;   // probabilities are stored as fp16(1024 * a)
 static constexpr float LN_EPS = 1e-5f;
 
@@ -51,29 +52,32 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
 }
 
-template <int C, bool FIRST>
+template <int C, bool FIRST, int EIN>
 struct PassCfg {
+    static constexpr int NW = pass_warps(C);
     static constexpr int KS = C / 16;
     static constexpr int ROWB = C * 2;                       // x^ row bytes
     static constexpr int XT_BYTES = 16 * ROWB;               // x^ tile (16 px) bytes
-    static constexpr int STAGE_BYTES = FIRST ? 16 * C * 4 : XT_BYTES;
-    static constexpr int NST = FIRST ? (C == 128 ? 3 : 2) : (C == 128 ? 6 : 4);
+    static constexpr int STAGE_BYTES = FIRST ? 16 * C * EIN : XT_BYTES;   // EIN = input element bytes (4 fp32, 2 bf16)
+    static constexpr int NST = (FIRST && EIN == 4) ? (C == 128 ? 3 : 2) : (C == 128 ? 6 : 4);
     static constexpr int NQB = (C == 128) ? 2 : 1;           // q~ buffers (double-buffered if room)
     static constexpr int NREG = KS * 4;
     static constexpr int OFF_STAGES = 0;
-    static constexpr int OFF_RED = PASS_WARPS * NST * STAGE_BYTES;
-    static constexpr int RED_BYTES = 4 * NREG * 32 * 4;
+    static constexpr int OFF_RED = NW * NST * STAGE_BYTES;
+    static constexpr int RED_BYTES = (NW / 2) * NREG * 32 * 4;
     static constexpr int OFF_QF = OFF_RED + RED_BYTES;
     static constexpr int QF_BYTES = 2 * 8 * C * 2 + 32;      // hi + lo + 8 fp32 logit biases
     static constexpr int OFF_LN = OFF_QF + NQB * QF_BYTES;
     static constexpr int OFF_CSW = OFF_LN;
-    static constexpr int OFF_BARS = OFF_CSW + 8 * 8 * 4;
-    static constexpr int SMEM = OFF_BARS + PASS_WARPS * NST * 8;
+    static constexpr int OFF_BARS = OFF_CSW + NW * 8 * 4;
+    static constexpr int SMEM = OFF_BARS + NW * NST * 8;
+    static_assert(SMEM <= 232448, "pass kernel: shared memory budget");
 };
 
-template <int C, bool FIRST>
-__global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassParams p) {
-    using Cfg = PassCfg<C, FIRST>;
+template <int C, bool FIRST, int EIN>
+__global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SAPassParams p) {
+    using Cfg = PassCfg<C, FIRST, EIN>;
+    constexpr int PASS_WARPS = Cfg::NW, PASS_THREADS = PASS_WARPS * 32;
     constexpr int KS = Cfg::KS, ROWB = Cfg::ROWB, XT_BYTES = Cfg::XT_BYTES;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES, NST = Cfg::NST, NREG = Cfg::NREG, NQB = Cfg::NQB;
 
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
 
     const int N = p.N, K = p.K;
     const int items = p.nframes * p.nchunk;
-    const int nbw = p.chunk_px >> 7;                 // 16-px tiles per warp per item
+    const int nbw = p.chunk_px / (16 * PASS_WARPS);  // 16-px tiles per warp per item
     const int tiles_chunk = p.chunk_px >> 4;
     const int tiles_frame = p.nchunk * tiles_chunk;
     const int my_items = (items > (int)blockIdx.x) ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -100,7 +104,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
     __syncthreads();
     if (my_items == 0) return;
 
-    const uint64_t pol = (FIRST || (p.dbg & 8)) ? l2_policy_evict_first() : l2_policy_evict_last();
+    // later passes re-read the x^ ring: keep it in L2 only if it can fit there
+    const bool ring_fits_l2 = (size_t)p.xhat_frames * p.n16 * C * 2 <= ((size_t)48 << 20);
+    const uint64_t pol = (FIRST || !ring_fits_l2) ? l2_policy_evict_first() : l2_policy_evict_last();
 
     auto issue = [&](uint32_t n) {
         if (n < total_tiles && lane == 0) {
@@ -117,8 +123,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
                 const void* src;
                 uint32_t bytes;
                 if (FIRST) {
-                    src = p.feats + (size_t)f * p.feat_bstride + (size_t)px0 * C;
-                    bytes = (uint32_t)nvalid * C * 4;
+                    src = reinterpret_cast<const unsigned char*>(p.feats) +
+                          ((size_t)f * p.feat_bstride + (size_t)px0 * C) * EIN;
+                    bytes = (uint32_t)nvalid * C * EIN;
                 } else {
                     src = p.xhat + ((size_t)(f % p.xhat_frames) * tiles_frame + tb) * (16 * C);
                     bytes = XT_BYTES;
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
                     //  land on raw rows 4h..4h+3, which are already in registers)
                     if (nvalid < 16) {
                         // ragged tail: zero the missing raw rows so they normalise to t = 0
-                        float4* z = reinterpret_cast<float4*>(stg + (size_t)nvalid * C * 4);
-                        for (int i = lane; i < (16 - nvalid) * (C / 4); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4* z = reinterpret_cast<float4*>(stg + (size_t)nvalid * C * EIN);
+                        for (int i = lane; i < (16 - nvalid) * (C * EIN / 16); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         __syncwarp();
                     }
 #pragma unroll
@@ -207,11 +214,17 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
                             const int row = 8 * hf + 4 * rr + pxi;
-                            const float* tp = reinterpret_cast<const float*>(stg) + row * C + 4 * ch8;
+                            const unsigned char* tp = stg + (size_t)(row * C + 4 * ch8) * EIN;
 #pragma unroll
                             for (int i = 0; i < C / 32; ++i) {
-                                const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tp + 32 * i);
-                                v[rr][2 * i] = q.x; v[rr][2 * i + 1] = q.y;
+                                if (EIN == 4) {
+                                    const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tp + 32 * i * 4);
+                                    v[rr][2 * i] = q.x; v[rr][2 * i + 1] = q.y;
+                                } else {            // bf16: the fp32 bit pattern is the 16 bits shifted up
+                                    const uint2 q = *reinterpret_cast<const uint2*>(tp + 32 * i * 2);
+                                    v[rr][2 * i] = pack2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
+                                    v[rr][2 * i + 1] = pack2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+                                }
                             }
                         }
                         __syncwarp();
@@ -259,7 +272,10 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
                 }
                 const uint32_t tile_u32 = smem_u32(stg);
                 // ---- logits: 16 pixels x 8 slots, log2 domain (scale folded into q~) ----
+                // four independent accumulator chains (hi/lo x even/odd k-step): legacy HMMA has a long
+                // dependent-issue latency on sm_100, so short chains matter more than instruction count
                 float lgA[4] = {lb0, lb1, lb0, lb1}, lgB[4] = {0.f, 0.f, 0.f, 0.f};
+                float lgC[4] = {0.f, 0.f, 0.f, 0.f}, lgD[4] = {0.f, 0.f, 0.f, 0.f};
                 {
                     const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
                     const uint32_t rowa = tile_u32 + row * ROWB;
@@ -270,13 +286,13 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
                         ldsm_x4(a1, rowa + (((2 * ks + 2 + (lane >> 4)) ^ (row & 7)) << 4));
                         mma_f16(lgA, a0, bq_hi[ks][0], bq_hi[ks][1]);
                         mma_f16(lgB, a0, bq_lo[ks][0], bq_lo[ks][1]);
-                        mma_f16(lgA, a1, bq_hi[ks + 1][0], bq_hi[ks + 1][1]);
-                        mma_f16(lgB, a1, bq_lo[ks + 1][0], bq_lo[ks + 1][1]);
+                        mma_f16(lgC, a1, bq_hi[ks + 1][0], bq_hi[ks + 1][1]);
+                        mma_f16(lgD, a1, bq_lo[ks + 1][0], bq_lo[ks + 1][1]);
                     }
                 }
                 float lg[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) lg[e] = lgA[e] + lgB[e];
+                for (int e = 0; e < 4; ++e) lg[e] = (lgA[e] + lgC[e]) + (lgB[e] + lgD[e]);
                 const int pxa = px0 + g, pxb = pxa + 8;
                 float pa0, pa1, pb0, pb1;
                 {
@@ -384,16 +400,25 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
 #pragma unroll
                     for (int e = 0; e < 4; ++e) uacc[cb][e] += red[(slot * NREG + cb * 4 + e) * 32 + lane];
             };
-            if (warp >= 4) put(warp - 4);
+            // tree over PASS_WARPS warps (8: 4-2-1, 12: 6-3-(1+2)); a warp only overwrites a slot it
+            // has already consumed itself
+            constexpr int H1 = PASS_WARPS / 2, H2 = PASS_WARPS / 4;
+            if (warp >= H1) put(warp - H1);
             __syncthreads();
-            if (warp < 4) add(warp);
-            if (warp == 2 || warp == 3) put(warp);
+            if (warp < H1) add(warp);
+            if (warp >= H2 && warp < H1) put(warp);
             __syncthreads();
-            if (warp < 2) add(2 + warp);
-            if (warp == 1) put(1);
+            if (PASS_WARPS == 8) {
+                if (warp < 2) add(2 + warp);
+                if (warp == 1) put(1);
+            } else {
+                if (warp < 3) add(3 + warp);
+                if (warp == 1 || warp == 2) put(warp);
+            }
             __syncthreads();
             if (warp == 0) {
                 add(1);
+                if (PASS_WARPS == 12) add(2);
 #pragma unroll
                 for (int cb = 0; cb < KS; ++cb)
 #pragma unroll
@@ -419,22 +444,27 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) sa_pass_kernel(const SAPassPa
     }
 }
 
-template <int C, bool FIRST>
+template <int C, bool FIRST, int EIN>
 static cudaError_t pass_launch_t(const SAPassParams& p, int sms, cudaStream_t st) {
-    using Cfg = PassCfg<C, FIRST>;
-    auto kern = sa_pass_kernel<C, FIRST>;
+    using Cfg = PassCfg<C, FIRST, EIN>;
+    auto kern = sa_pass_kernel<C, FIRST, EIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
     const int items = p.nframes * p.nchunk;
     const int grid = items < sms ? items : sms;
-    kern<<<grid, PASS_THREADS, Cfg::SMEM, st>>>(p);
+    kern<<<grid, Cfg::NW * 32, Cfg::SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, int smem_limit, cudaStream_t st) {
     (void)smem_limit;
-    if (C == 128) return first ? pass_launch_t<128, true>(p, sms, st) : pass_launch_t<128, false>(p, sms, st);
-    return first ? pass_launch_t<192, true>(p, sms, st) : pass_launch_t<192, false>(p, sms, st);
+    const bool bf16 = p.feat_esize == 2;
+    if (C == 128) {
+        if (!first) return pass_launch_t<128, false, 4>(p, sms, st);
+        return bf16 ? pass_launch_t<128, true, 2>(p, sms, st) : pass_launch_t<128, true, 4>(p, sms, st);
+    }
+    if (!first) return pass_launch_t<192, false, 4>(p, sms, st);
+    return bf16 ? pass_launch_t<192, true, 2>(p, sms, st) : pass_launch_t<192, true, 4>(p, sms, st);
 }
 
 }  // namespace sfb

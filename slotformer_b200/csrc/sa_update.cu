@@ -493,9 +493,10 @@ void sa_workspace_layout(int B, int chunk_frames, int N, int C, int D, int DM, i
     ws->w1 = take((size_t)DM * D * 2 * 2);
     ws->w2 = take((size_t)D * DM * 2 * 2);
     ws->wbeta = take((size_t)D * 4);
-    // pixel chunking: 1024-pixel items (8 warps x 8 tiles), smaller for small N
-    int chunk_px = 1024;
-    while (chunk_px > 128 && chunk_px / 2 >= N) chunk_px /= 2;
+    // items of 16 px x 8 warps (pass kernel) x up to 8 tiles per warp
+    const int unit = 16 * 8;
+    int chunk_px = 8 * unit;
+    while (chunk_px > unit && chunk_px / 2 >= N) chunk_px /= 2;
     ws->chunk_px = chunk_px;
     ws->nchunk = (N + chunk_px - 1) / chunk_px;
     ws->n16 = ws->nchunk * chunk_px;

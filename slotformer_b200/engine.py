@@ -14,6 +14,7 @@ _LIB_PATH = os.path.join(_HERE, 'lib', 'libsfb200.so')
 _lib = None
 
 SFB_DTYPE_F32 = 0
+SFB_DTYPE_BF16 = 1
 SFB_RO_SLIDE = 0
 SFB_RO_GROW = 1
 RO_MAX_LAYERS = 16
@@ -161,7 +162,11 @@ class SlotAttentionEngine:
         Returns slots [B,K,D] (and seg mask [B,K,N] if ``return_mask``).
         """
         lib = load()
-        _require_cuda_f32('inputs', feats)
+        if isinstance(feats, torch.Tensor) and feats.dtype == torch.bfloat16 and feats.is_cuda:
+            feat_dtype = SFB_DTYPE_BF16
+        else:
+            _require_cuda_f32('inputs', feats)
+            feat_dtype = SFB_DTYPE_F32
         _require_cuda_f32('slots', slots)
         if feats.dim() != 3 or slots.dim() != 3 or feats.shape[0] != slots.shape[0]:
             raise SfbError(f'bad shapes: inputs {tuple(feats.shape)}, slots {tuple(slots.shape)}')
@@ -173,8 +178,8 @@ class SlotAttentionEngine:
         slots = slots.contiguous()
         dev = feats.device
         if B == 0:
-            out = feats.new_zeros((0, K, D))
-            return (out, feats.new_zeros((0, K, N))) if return_mask else out
+            out = slots.new_zeros((0, K, D))
+            return (out, slots.new_zeros((0, K, N))) if return_mask else out
         ws_bytes = int(lib.sfb_sa_workspace_bytes(B, N, C, D, int(mlp_hidden_size),
                                                   int(num_iterations), int(chunk_frames)))
         if ws_bytes == 0:
@@ -199,7 +204,7 @@ class SlotAttentionEngine:
                                           self._ws.numel(), _stream(dev)))
                 self._key = key
             rc = lib.sfb_sa_forward(
-                feats.data_ptr(), SFB_DTYPE_F32, bstride, slots.data_ptr(), out.data_ptr(),
+                feats.data_ptr(), feat_dtype, bstride, slots.data_ptr(), out.data_ptr(),
                 mask.data_ptr() if return_mask else None, ctypes.byref(cw), B, N, C, D,
                 int(mlp_hidden_size), K, int(num_iterations), float(eps), int(chunk_frames),
                 self._ws.data_ptr(), ws_bytes, _stream(dev))

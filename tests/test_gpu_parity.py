@@ -65,6 +65,20 @@ def test_slot_attention_chunked_and_strided_input():
     assert rel_max(out16.cpu().numpy(), g['slots_f64']) < 1e-3
 
 
+def test_slot_attention_bf16_features():
+    """bf16 feature grids (BASELINE config 3): same result as the oracle on the bf16-rounded input."""
+    c, w, feats, slots = cases.sa_case('sa_cfg3')
+    fb = torch.from_numpy(feats).to(DEV).to(torch.bfloat16)
+    ref = O.slot_attention(fb.float().cpu().numpy(), slots, w, c['iters'])
+    m = sa_module(c, w, DEV)
+    with torch.no_grad():
+        out = m(fb, torch.from_numpy(slots).to(DEV))
+        ragged = m(fb[:, :1000].contiguous(), torch.from_numpy(slots).to(DEV))
+    assert rel_max(out.cpu().numpy(), ref) < 1e-3
+    ref_r = O.slot_attention(fb[:, :1000].float().cpu().numpy(), slots, w, c['iters'])
+    assert rel_max(ragged.cpu().numpy(), ref_r) < 1e-3
+
+
 def test_slot_attention_full_size_properties():
     """BASELINE config-2 size (384 frames x 4096 x 128): determinism, batch independence,
     pixel-permutation invariance (Slot Attention is a set function of the pixels)."""
@@ -137,6 +151,25 @@ def test_rollout_full_size_properties():
         x2 = torch.cat([x[:, 1:], a[:, :1]], dim=1)
         b = m(x2, 9)
     assert torch.equal(b, a[:, 1:])
+
+
+@pytest.mark.parametrize('name,B', [('ro_cfg3', 32), ('ro_cfg4', 16), ('ro_cfg5', 256)])
+def test_rollout_baseline_configs_full_batch(name, B):
+    """BASELINE configs 3-5 at their full batch sizes and horizons (44 / 20 / 64 steps): finite,
+    deterministic, clip-independent; the first clips reproduce the reference golden."""
+    c, w, hist = cases.ro_case(name)
+    g = golden(name)
+    m = ro_module(c, w, DEV, enc_t_pe=g['enc_t_pe'])
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn((B,) + hist.shape[1:], device=DEV, generator=gen)
+    x[:hist.shape[0]] = torch.from_numpy(hist).to(DEV)
+    with torch.no_grad():
+        a = m(x, c['pred_len'])
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, m(x, c['pred_len']))
+        sub = m(x[[B - 1, 1]].contiguous(), c['pred_len'])
+    assert torch.equal(sub, a[[B - 1, 1]])
+    assert rel_max(a[:hist.shape[0]].cpu().numpy(), g['pred_f64']) < 4e-3
 
 
 def test_engine_rejects_cpu_tensors_and_bad_shapes():
