@@ -22,6 +22,8 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--use_fast_math', '-Xptxas', '-v']
 # --use_fast_math would change expf/division semantics in the slot update; keep IEEE there
 NVCC_FLAGS.remove('--use_fast_math')
+if os.environ.get('SFB_FINE_PROF'):      # per-role clock64 trace of one rollout layer (scripts/prof_ro_fine.py)
+    NVCC_FLAGS.append('-DSFB_FINE_PROF')
 
 
 def _nvcc():

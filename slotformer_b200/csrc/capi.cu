@@ -215,9 +215,15 @@ static size_t ro_ws_elems(int Ds, int d, int F, int layers) {
            (size_t)layers * (pad128(3 * d) * d + pad128(d) * d + pad128(F) * d + pad128(d) * F);
 }
 
+// fp32 per-layer parameter blocks that follow the fp16 weights (16-byte aligned)
+static size_t ro_par_floats(int d, int F) { return (size_t)9 * d + F; }
+static size_t ro_par_offset(int Ds, int d, int F, int layers) {
+    return (ro_ws_elems(Ds, d, F, layers) * sizeof(__half) + 255) / 256 * 256;
+}
+
 size_t sfb_rollout_workspace_bytes(int Ds, int d, int F, int num_layers) {
     if (Ds <= 0 || d <= 0 || F <= 0 || num_layers <= 0) return 0;
-    return ro_ws_elems(Ds, d, F, num_layers) * sizeof(__half);
+    return ro_par_offset(Ds, d, F, num_layers) + (size_t)num_layers * ro_par_floats(d, F) * sizeof(float);
 }
 
 // workspace layout (fp16): w_in [d][Ds] | w_out [Ds][d] | per layer: wqkv [3d][d], wo [d][d], w1 [F][d], w2 [d][F]
@@ -252,6 +258,20 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
         if ((rc = run(ly.linear1_weight, F, d))) return rc;
         if ((rc = run(ly.linear2_weight, d, F))) return rc;
     }
+    // biases + LayerNorm affine of every layer as one contiguous fp32 block (staged with one bulk copy per layer)
+    float* par = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ro_par_offset(Ds, d, F, w->num_layers));
+    for (int l = 0; l < w->num_layers; ++l) {
+        const sfb_ro_layer& ly = w->layers[l];
+        const float* srcs[8] = {ly.self_attn_in_proj_bias, ly.self_attn_out_proj_bias, ly.linear1_bias, ly.linear2_bias,
+                                ly.norm1_weight, ly.norm1_bias, ly.norm2_weight, ly.norm2_bias};
+        const int lens[8] = {3 * d, d, F, d, d, d, d, d};
+        for (int i = 0; i < 8; ++i) {
+            if (!srcs[i]) return SFB_E_NULL;
+            e = cudaMemcpyAsync(par, srcs[i], (size_t)lens[i] * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return cuda_err(e);
+            par += lens[i];
+        }
+    }
     return SFB_OK;
 }
 
@@ -279,6 +299,7 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     p.w_in = ws; ws += pad128(d) * Ds;
     p.w_out = ws; ws += pad128(Ds) * d;
     p.b_in = w->in_proj_bias; p.b_out = w->out_proj_bias; p.pe = w->enc_pe;
+    p.par_g = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + ro_par_offset(Ds, d, F, w->num_layers));
     for (int l = 0; l < w->num_layers; ++l) {
         const sfb_ro_layer& s = w->layers[l];
         sfb::ROLayer& t = p.layer[l];

@@ -8,6 +8,11 @@ static constexpr int RO_WARPS = 8;            // consumer warps
 static constexpr int RO_THREADS = RO_WARPS * 32;
 static constexpr float RO_LN_EPS = 1e-5f;
 
+// 2^x on the SFU, one instruction (exp2f adds denormal range handling that softmax does not need); 2^-inf = 0
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
 // LayerNorm rows [0, L) of h (fp32, stride d) -> fp16 rows of `out` (stride ldo); rows [L, Lp) = 0
 template <int DMODEL, int RPW, class Addr>
 __device__ __forceinline__ void ln_to_half(const float* h, unsigned char* out, Addr addr, int L, int Lp,
@@ -55,6 +60,120 @@ __device__ __forceinline__ void ln_to_half(const float* h, unsigned char* out, A
         }
     }
   }
+}
+
+// Same, one lane per 4 consecutive features: 128-bit row loads, 64-bit packed fp16 stores
+// (a quarter of the load/store/address instructions of ln_to_half).
+template <int DMODEL, int RPW, class Addr>
+__device__ __forceinline__ void ln_to_half_v(const float* h, unsigned char* out, Addr addr, int L, int Lp,
+                                             const float* gw, const float* gb, int warp, int lane) {
+    constexpr int NV = DMODEL / 128;
+    float4 gmm[NV], bta[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        gmm[i] = *reinterpret_cast<const float4*>(gw + 4 * lane + 128 * i);
+        bta[i] = *reinterpret_cast<const float4*>(gb + 4 * lane + 128 * i);
+    }
+    for (int row0 = 0; row0 < Lp; row0 += RO_WARPS * RPW) {
+        float4 v[RPW][NV];
+        float s[RPW], q[RPW];
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const int r = row0 + warp + RO_WARPS * j;
+            s[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                v[j][i] = (r < L) ? *reinterpret_cast<const float4*>(h + r * DMODEL + 4 * lane + 128 * i)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                s[j] += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const float mu = s[j] * (1.f / DMODEL);
+            q[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                v[j][i].x -= mu; v[j][i].y -= mu; v[j][i].z -= mu; v[j][i].w -= mu;
+                q[j] = fmaf(v[j][i].x, v[j][i].x, q[j]); q[j] = fmaf(v[j][i].y, v[j][i].y, q[j]);
+                q[j] = fmaf(v[j][i].z, v[j][i].z, q[j]); q[j] = fmaf(v[j][i].w, v[j][i].w, q[j]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const int r = row0 + warp + RO_WARPS * j;
+            if (r < Lp) {
+                const float rstd = (r < L) ? rsqrtf(q[j] * (1.f / DMODEL) + RO_LN_EPS) : 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    uint2 pk = make_uint2(0u, 0u);
+                    if (r < L) {
+                        pk.x = pack_h2(fmaf(v[j][i].x * rstd, gmm[i].x, bta[i].x), fmaf(v[j][i].y * rstd, gmm[i].y, bta[i].y));
+                        pk.y = pack_h2(fmaf(v[j][i].z * rstd, gmm[i].z, bta[i].z), fmaf(v[j][i].w * rstd, gmm[i].w, bta[i].w));
+                    }
+                    *reinterpret_cast<uint2*>(out + addr(r, 4 * lane + 128 * i)) = pk;
+                }
+            }
+        }
+    }
+}
+
+// LayerNorm with 4 lanes per row (8 rows per warp, 64 rows per pass of the 8 warps): two shuffle steps per
+// reduction and a single pass for every supported window.  Lane j of a row group owns the float4 chunks at
+// features 4j + 16i; rows are HPAD floats apart beyond DMODEL so that the two rows of a quarter-warp hit
+// different banks.  Four independent accumulators keep the per-lane sums off one dependent chain.
+template <int DMODEL, int HPAD, class Addr>
+__device__ __forceinline__ void ln_to_half_q(const float* h, unsigned char* out, Addr addr, int L, int Lp,
+                                             const float* gw, const float* gb, int warp, int lane) {
+    constexpr int NV = DMODEL / 16, HS = DMODEL + HPAD;
+    const int j = lane & 3, rsub = lane >> 2;
+    for (int row0 = 0; row0 < Lp; row0 += RO_WARPS * 8) {
+        if (row0 + warp * 8 >= Lp) break;            // warp-uniform
+        const int r = row0 + warp * 8 + rsub;
+        const bool valid = r < L;
+        float4 v[NV];
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i] = valid ? *reinterpret_cast<const float4*>(h + r * HS + 4 * j + 16 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s4[i & 3] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float mu = s * (1.f / DMODEL);
+        float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x -= mu; v[i].y -= mu; v[i].z -= mu; v[i].w -= mu;
+            q4[i & 3] = fmaf(v[i].x, v[i].x, q4[i & 3]); q4[i & 3] = fmaf(v[i].y, v[i].y, q4[i & 3]);
+            q4[i & 3] = fmaf(v[i].z, v[i].z, q4[i & 3]); q4[i & 3] = fmaf(v[i].w, v[i].w, q4[i & 3]);
+        }
+        float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        if (r < Lp) {
+            const float rstd = valid ? rsqrtf(q * (1.f / DMODEL) + RO_LN_EPS) : 0.f;   // pad rows -> exact zeros
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gw + 4 * j + 16 * i);
+                const float4 b4 = *reinterpret_cast<const float4*>(gb + 4 * j + 16 * i);
+                const float z = valid ? 1.f : 0.f;
+                uint2 pk;
+                pk.x = pack_h2(fmaf(v[i].x * rstd, g4.x, b4.x * z), fmaf(v[i].y * rstd, g4.y, b4.y * z));
+                pk.y = pack_h2(fmaf(v[i].z * rstd, g4.z, b4.z * z), fmaf(v[i].w * rstd, g4.w, b4.w * z));
+                *reinterpret_cast<uint2*>(out + addr(r, 4 * j + 16 * i)) = pk;
+            }
+        }
+    }
 }
 
 // One (head, 16-query block) of softmax(Q K^T / sqrt(dh)) V.  Q/K/V live in `buf` (fp16, stride
@@ -192,11 +311,16 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
 #pragma unroll
         for (int nb = 0; nb < NKB; ++nb) {
             if (nb < nkb) {
-                const int c = 8 * nb + 2 * t4;
-                s[mb][nb][0] = (c < L) ? s[mb][nb][0] * sm_scale_log2 : -INFINITY;
-                s[mb][nb][1] = (c + 1 < L) ? s[mb][nb][1] * sm_scale_log2 : -INFINITY;
-                s[mb][nb][2] = (c < L) ? s[mb][nb][2] * sm_scale_log2 : -INFINITY;
-                s[mb][nb][3] = (c + 1 < L) ? s[mb][nb][3] * sm_scale_log2 : -INFINITY;
+                if (8 * nb + 8 <= L) {        // block of valid keys only (warp-uniform): no masking work
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s[mb][nb][e] *= sm_scale_log2;
+                } else {
+                    const int c = 8 * nb + 2 * t4;
+                    s[mb][nb][0] = (c < L) ? s[mb][nb][0] * sm_scale_log2 : -INFINITY;
+                    s[mb][nb][1] = (c + 1 < L) ? s[mb][nb][1] * sm_scale_log2 : -INFINITY;
+                    s[mb][nb][2] = (c < L) ? s[mb][nb][2] * sm_scale_log2 : -INFINITY;
+                    s[mb][nb][3] = (c + 1 < L) ? s[mb][nb][3] * sm_scale_log2 : -INFINITY;
+                }
                 m0[mb] = fmaxf(m0[mb], fmaxf(s[mb][nb][0], s[mb][nb][1]));
                 m1[mb] = fmaxf(m1[mb], fmaxf(s[mb][nb][2], s[mb][nb][3]));
             }
@@ -216,13 +340,11 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
 #pragma unroll
         for (int nb = 0; nb < NKB; ++nb) {
             if (nb < nkb) {
-                const float e0 = exp2f(s[mb][nb][0] - m0[mb]), e1 = exp2f(s[mb][nb][1] - m0[mb]);
-                const float e2 = exp2f(s[mb][nb][2] - m1[mb]), e3 = exp2f(s[mb][nb][3] - m1[mb]);
-                const __half2 h01 = __floats2half2_rn(e0, e1), h23 = __floats2half2_rn(e2, e3);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                l0[mb] += f01.x + f01.y; l1[mb] += f23.x + f23.y;
-                pf[mb][nb][0] = *reinterpret_cast<const uint32_t*>(&h01);
-                pf[mb][nb][1] = *reinterpret_cast<const uint32_t*>(&h23);
+                const float e0 = fast_exp2(s[mb][nb][0] - m0[mb]), e1 = fast_exp2(s[mb][nb][1] - m0[mb]);
+                const float e2 = fast_exp2(s[mb][nb][2] - m1[mb]), e3 = fast_exp2(s[mb][nb][3] - m1[mb]);
+                l0[mb] += e0 + e1; l1[mb] += e2 + e3;
+                pf[mb][nb][0] = pack_h2(e0, e1);
+                pf[mb][nb][1] = pack_h2(e2, e3);
             } else {
                 pf[mb][nb][0] = pf[mb][nb][1] = 0u;
             }

@@ -22,6 +22,7 @@ struct ROParams {
     const __half* w_out; // packed [Ds][d]
     const float* b_out;
     const float* pe;     // [pe_tokens][d]
+    const float* par_g;  // [layers][par_floats]: bqkv | bo | b1 | b2 | ln1w | ln1b | ln2w | ln2b (workspace, fp32)
     int B, hist_tokens, K, Ds, d, F, heads, layers, pred_len, mode, cond_tokens, pe_tokens;
     int hg;              // heads per attention group
     int fc;              // FFN hidden chunk (columns)
@@ -30,6 +31,7 @@ struct ROParams {
     int par_floats;      // per-layer parameter block (biases + LayerNorm) staged in smem
     int par_double;      // 1: double-buffered (next layer prefetched), 0: single buffer (big shapes)
     int nstage;          // weight-panel ring depth
+    int stage_tiles;     // engine B: 16 KB weight tiles per ring stage (1 or 2)
     uint32_t off_h, off_a, off_b, off_bars, off_ring, off_par;   // shared-memory byte offsets
     unsigned long long* prof;       // optional timeline buffer (debug)
     int prof_cap;

@@ -22,11 +22,13 @@
 namespace sfb {
 
 static constexpr int RU_TILE_BYTES = 16384;                 // one 128 x 64 weight tile
-static constexpr int RU_STAGE_TILES = 2;                    // k-adjacent tiles per ring stage
-static constexpr int RU_STAGE_BYTES = RU_STAGE_TILES * RU_TILE_BYTES;
+static constexpr int RU_HPAD = 16;                          // fp32 pad of a residual-stream row (bank spread for 4-lane row groups)
+static constexpr int RU_MAX_STAGE_TILES = 2;                // k-adjacent tiles per ring stage: 1 or 2 (plan)
 static constexpr int RU_TILE_HALVES = 8192;
 static constexpr int RU_SYNC_THREADS = RO_THREADS + 32;   // compute warps + MMA warp
-static constexpr int RU_THREADS = RO_THREADS + 64;
+static constexpr int RU_THREADS = RO_THREADS + 128;   // + one warpgroup: TMA producer, MMA issuer, two idle warps
+static constexpr int RU_REGS_COMPUTE = 216;          // setmaxnreg: the epilogue / attention warps take what the
+static constexpr int RU_REGS_SERVICE = 72;           // service warpgroup gives up (8*32*216 + 4*32*72 = 64512)
 
 struct UOp {
     const __half* base;   // packed matrix (ro_pack2 layout)
@@ -35,12 +37,63 @@ struct UOp {
     int kb0, nkb;         // k-block range
 };
 
+// barrier words (uint64 each) inside the `bars` region
+static constexpr int RU_BAR_FULL = 0;     // [8] weight stage filled (TMA complete_tx)
+static constexpr int RU_BAR_EMPTY = 8;    // [8] weight stage consumed (tcgen05.commit)
+static constexpr int RU_BAR_ACC = 16;     // [9] accumulator tile t complete; [8] = second GEMM of the fused FFN
+static constexpr int RU_BAR_RDY = 25;     // [8] hidden k-block pair j written by the epilogue warps
+static constexpr int RU_BAR_CHUNK = 33;   // FFN chunk boundary: the chunk's W2 MMAs have read the hidden tile
+static constexpr int RU_BAR_PAR = 34;     // [2] per-layer parameter block landed
+static constexpr int RU_BAR_TMEM = 36;    // TMEM base address slot
+static constexpr int RU_BAR_WORDS = 40;
+static constexpr int RU_ACC2 = 8;
+
 struct BRing {
     unsigned char* stages;
     uint64_t* full;
     uint64_t* empty;
     int nstage;
+    int stage_tiles;      // weight tiles (16 KB) per stage
 };
+
+// arguments of the fused feed-forward block  h += W2 relu(W1 x^ + b1) + b2  (one hidden chunk)
+struct FfnArgs {
+    const __half *w1, *w2;
+    const float *b1, *b2;      // smem copies (b1 indexed by absolute hidden feature)
+    int d, F, f0, fcw;         // model width, hidden width, chunk start / width
+    int Lp, kbb;
+    uint32_t x_u32, y_u32;
+    unsigned char* yb;
+    float* h;
+    uint32_t acc2_col;         // TMEM column of the W2 accumulator
+    bool first, last;          // first / last hidden chunk of the layer
+};
+
+// one lane polls, the rest of the warp sleeps at the warp barrier (8 pollers instead of 256)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) { while (!mbar_try_wait(bar, parity)) { } }
+    __syncwarp();      // lane 0's acquire + the warp barrier order the other lanes' accesses behind the phase
+}
+
+// fine-grained per-role trace (clock64 of this SM) of one layer, for the debug timeline only
+// (compiled in only with -DSFB_FINE_PROF: the trace state costs registers the attention phase needs)
+#ifdef SFB_FINE_PROF
+struct FineProf {
+    unsigned long long* buf;   // nullptr = off
+    int n, cap;
+    bool on;
+    __device__ __forceinline__ void mark(int tag) {
+        if (buf != nullptr && on && n < cap) buf[n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    }
+    __device__ __forceinline__ void enable(bool v) { on = v; }
+};
+#else
+struct FineProf {
+    __device__ __forceinline__ FineProf(unsigned long long*, int, int, bool) {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void enable(bool) {}
+};
+#endif
 
 struct BProducer {
     static constexpr bool kCompute = false;
@@ -48,19 +101,33 @@ struct BProducer {
     uint32_t pidx;
     uint64_t pol;
     int dbg;
-    template <class Pre, class Epi>
-    __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) {
+    FineProf fp;
+    __device__ __forceinline__ void emit(const UOp& op) {
         for (int t = 0; t < op.ntile; ++t)
-            for (int kb = 0; kb < op.nkb; kb += RU_STAGE_TILES, ++pidx) {
-                const int nk = (op.nkb - kb) < RU_STAGE_TILES ? (op.nkb - kb) : RU_STAGE_TILES;
+            for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles, ++pidx) {
+                const int nk = (op.nkb - kb) < ring.stage_tiles ? (op.nkb - kb) : ring.stage_tiles;
                 const int s = pidx % ring.nstage;
-                mbar_wait_sleep(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+                // spin (no back-off): a sleeping producer adds its wake-up latency to every refill of the ring
+                fp.mark(1);
+                mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+                fp.mark(2);
                 if (dbg & 1) { mbar_arrive(&ring.full[s]); continue; }
                 mbar_arrive_expect_tx(&ring.full[s], nk * RU_TILE_BYTES);
-                bulk_g2s(ring.stages + (size_t)s * RU_STAGE_BYTES,
+                bulk_g2s(ring.stages + (size_t)s * ring.stage_tiles * RU_TILE_BYTES,
                          op.base + ((size_t)(op.tile0 + t) * op.kpt + op.kb0 + kb) * RU_TILE_HALVES,
                          nk * RU_TILE_BYTES, &ring.full[s], pol);
             }
+    }
+    template <class Pre, class Epi>
+    __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) { emit(op); }
+    template <int HMAX>
+    __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int, int, const float*, float, int, unsigned char*) { emit(op); }
+    // weight order of the fused FFN: every W1 tile of the chunk, then the W2 k-block pairs in tile order
+    template <int HMAX>
+    __device__ __forceinline__ void ffn(const FfnArgs& a) {
+        const int nt = a.fcw >> 7, dt = a.d >> 7, kpd = a.d >> 6;
+        emit(UOp{a.w1, kpd, a.f0 >> 7, nt, 0, kpd});
+        for (int j = 0; j < nt; ++j) emit(UOp{a.w2, a.F >> 6, 0, dt, (a.f0 >> 6) + 2 * j, 2});
     }
     __device__ __forceinline__ void sync() {}
 };
@@ -70,43 +137,80 @@ struct BMma {
     BRing ring;
     uint32_t pidx;
     uint32_t tmem;
-    uint64_t* accfull;
+    uint64_t* bars;
+    uint32_t rdypar;          // bit j = parity of the next completion of rdy[j]
     int lane;
     int dbg;
-    // b_u32: smem address of the token operand (k-block 0), kblock_bytes apart per 64 k
-    template <class Pre, class Epi>
-    __device__ __forceinline__ void gemm(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, Pre, Epi) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, ntok);
-            for (int t = 0; t < op.ntile; ++t)
-                for (int kb = 0; kb < op.nkb; kb += RU_STAGE_TILES, ++pidx) {
-                    const int nk = (op.nkb - kb) < RU_STAGE_TILES ? (op.nkb - kb) : RU_STAGE_TILES;
-                    const int s = pidx % ring.nstage;
-                    mbar_wait_sleep(&ring.full[s], (pidx / ring.nstage) & 1);
-                    tcgen05_fence_after();
-                    // descriptors are built once per stage; a K step of 16 (32 B) or the next k tile only
-                    // advances the 16-byte-granular start-address field
-                    const uint64_t da0 = umma_smem_desc(smem_u32(ring.stages + (size_t)s * RU_STAGE_BYTES));
-                    const uint64_t db0 = umma_smem_desc(b_u32 + kb * kblock_bytes);
-                    const uint32_t dtm = tmem + (uint32_t)(t * ntok);
+    FineProf fp;
+    // MMAs of `op` into TMEM columns dcol + t * ntok (tile t); b_u32: smem address of the token operand's
+    // k-block 0 of this op, kblock_bytes apart per 64 k.  acc_first: the first k-step accumulates too.
+    __device__ __forceinline__ void issue(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, uint32_t dcol,
+                                          bool acc_first, bool commit_tiles) {
+        const uint32_t idesc = umma_idesc_f16(128, ntok);
+        for (int t = 0; t < op.ntile; ++t) {
+            for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles, ++pidx) {
+                const int nk = (op.nkb - kb) < ring.stage_tiles ? (op.nkb - kb) : ring.stage_tiles;
+                const int s = pidx % ring.nstage;
+                fp.mark(1);
+                mbar_wait(&ring.full[s], (pidx / ring.nstage) & 1);
+                fp.mark(2);
+                tcgen05_fence_after();
+                // descriptors are built once per stage; a K step of 16 (32 B) or the next k tile only
+                // advances the 16-byte-granular start-address field
+                const uint64_t da0 = umma_smem_desc(smem_u32(ring.stages + (size_t)s * ring.stage_tiles * RU_TILE_BYTES));
+                const uint64_t db0 = umma_smem_desc(b_u32 + kb * kblock_bytes);
+                const uint32_t dtm = tmem + dcol + (uint32_t)(t * ntok);
+                if (elect_one()) {
                     if (!(dbg & 2)) {
 #pragma unroll
-                        for (int kk = 0; kk < RU_STAGE_TILES; ++kk) {
+                        for (int kk = 0; kk < RU_MAX_STAGE_TILES; ++kk) {
                             if (kk < nk) {
                                 const uint64_t dbk = db0 + (uint64_t)((kk * kblock_bytes) >> 4);
 #pragma unroll
                                 for (int k4 = 0; k4 < 4; ++k4)
                                     umma_f16(dtm, da0 + (uint64_t)((kk * RU_TILE_BYTES + k4 * 32) >> 4),
-                                             dbk + (uint64_t)((k4 * 32) >> 4), idesc, (kb | kk | k4) != 0);
+                                             dbk + (uint64_t)((k4 * 32) >> 4), idesc, acc_first || (kb | kk | k4) != 0);
                             }
                         }
                     }
-                    if (dbg & 8) mbar_arrive(&ring.empty[s]);   // (timing experiment only: frees the stage early)
-                    else umma_commit(&ring.empty[s]);           // stage is free once these MMAs have read it
+                    umma_commit(&ring.empty[s]);           // stage is free once these MMAs have read it
                 }
-            umma_commit(accfull);                     // accumulators of this GEMM are complete
+                __syncwarp();
+                fp.mark(3);
+            }
+            if (commit_tiles) commit(&bars[RU_BAR_ACC + t]);   // this tile's accumulator is complete
         }
+    }
+    __device__ __forceinline__ void commit(uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
         __syncwarp();
+    }
+    template <class Pre, class Epi>
+    __device__ __forceinline__ void gemm(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, Pre, Epi) {
+        issue(op, b_u32, kblock_bytes, ntok, 0u, false, true);      // whole warp, uniform; one elected lane issues
+    }
+    template <int HMAX>
+    __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, const float*, float,
+                                             int, unsigned char*) {
+        issue(op, b_u32, kblock_bytes, ntok, 0u, false, true);
+    }
+    __device__ __forceinline__ void ffn2_part(const FfnArgs& a, int j) {
+        fp.mark(4);
+        mbar_wait(&bars[RU_BAR_RDY + j], (rdypar >> j) & 1u);
+        fp.mark(5);
+        rdypar ^= 1u << j;
+        tcgen05_fence_after();
+        issue(UOp{a.w2, a.F >> 6, 0, a.d >> 7, (a.f0 >> 6) + 2 * j, 2}, a.y_u32 + (uint32_t)(2 * j * a.kbb), a.kbb, a.Lp,
+              a.acc2_col, !(a.first && j == 0), false);
+    }
+    // all W1 tiles first (they only need x^), then each W2 k-block pair as soon as the epilogue warps have
+    // written that hidden tile: the W2 MMAs of tile j overlap the epilogue of tile j+1
+    template <int HMAX>
+    __device__ __forceinline__ void ffn(const FfnArgs& a) {
+        const int nt = a.fcw >> 7, kpd = a.d >> 6;
+        issue(UOp{a.w1, kpd, a.f0 >> 7, nt, 0, kpd}, a.x_u32, a.kbb, a.Lp, 0u, false, true);
+        for (int j = 0; j < nt; ++j) ffn2_part(a, j);
+        commit(a.last ? &bars[RU_BAR_ACC + RU_ACC2] : &bars[RU_BAR_CHUNK]);
     }
     __device__ __forceinline__ void sync() {
         named_bar_sync(1, RU_SYNC_THREADS);
@@ -117,43 +221,164 @@ struct BMma {
 struct BCompute {
     static constexpr bool kCompute = true;
     uint32_t tmem;
-    uint64_t* accfull;
-    uint32_t ngemm;
+    uint64_t* bars;
+    uint32_t accpar;          // bit t = parity of the next completion of acc[t]
+    uint32_t chunkpar;
     int warp, lane;
     int dbg;
+    FineProf fp;
+    __device__ __forceinline__ void acc_wait(int t) {
+        fp.mark(1);
+        mbar_wait_warp(&bars[RU_BAR_ACC + t], (accpar >> t) & 1u, lane);
+        fp.mark(2);
+        accpar ^= 1u << t;
+        tcgen05_fence_after();
+    }
     // epi(feature, token8, values[8], pre(feature)): 8 consecutive tokens (token8 % 8 == 0) of one feature;
     // features of the warp's TMEM lane quadrant, one half of the tokens (warps w and w+4 share lanes)
     template <class Pre, class Epi>
-    __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int ntok, Pre pre, Epi epi) {
-        mbar_wait(accfull, ngemm & 1);
-        ++ngemm;
-        tcgen05_fence_after();
+    __device__ __forceinline__ void epi_tile(int t, uint32_t dcol, int ntok, Pre pre, Epi epi) {
+        if (dbg & 4) return;
         const int q = warp & 3, half = ntok >> 1, t0 = (warp >> 2) * half;
-        for (int t = 0; t < ((dbg & 4) ? 0 : op.ntile); ++t) {
-            const int f = t * 128 + 32 * q + lane;
-            const float pv = pre(f);
-            const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * ntok + t0);
-            for (int c0 = 0; c0 < half; c0 += 16) {
-                float v0[8], v1[8];
-                tmem_ld8(ta + c0, v0);
-                const bool two = (c0 + 8) < half;
-                if (two) tmem_ld8(ta + c0 + 8, v1);
-                tmem_ld_wait();
-                epi(f, t0 + c0, v0, pv);                 // 8 consecutive tokens, base a multiple of 8
-                if (two) epi(f, t0 + c0 + 8, v1, pv);
+        const int f = t * 128 + 32 * q + lane;
+        const float pv = pre(f);
+        const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + dcol + (uint32_t)t0;
+        float v[4][8];                               // up to 32 tokens per warp: every load first, one wait
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (8 * c < half) tmem_ld8(ta + 8 * c, v[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (8 * c < half) epi(f, t0 + 8 * c, v[c], pv);      // 8 consecutive tokens, base a multiple of 8
+    }
+    // fp16 epilogue of one 128-feature tile: (acc + bias) [* qscale for features < nscale] [relu] -> operand
+    // buffer `yb` (token rows, K-major swizzled).  16x256b TMEM loads give the stmatrix.trans fragment, so a
+    // 16-feature x 16-token block is one store instruction instead of 8 scattered 2-byte stores per thread.
+    template <int HMAX>
+    __device__ __forceinline__ void epi_tile_h16(int t, uint32_t dcol, int ntok, const float* bias, bool relu,
+                                                 float qscale, int nscale, unsigned char* yb, int kbb) {
+        if (dbg & 4) return;
+        const int q = warp & 3, half = ntok >> 1, t0 = (warp >> 2) * half;   // HMAX >= half: tokens per warp
+        const uint32_t yb_u32 = smem_u32(yb);
+        float v[2][HMAX / 2];        // [16-feature group][4 values per 8-token block]
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t ta = tmem + ((uint32_t)(32 * q + 16 * g) << 16) + dcol + (uint32_t)t0;
+#pragma unroll
+            for (int c0 = 0; c0 < HMAX; c0 += 16) {
+                if (c0 + 16 <= HMAX && c0 + 16 <= half) {
+                    float w[8];
+                    tmem_ld_16x256b_x2(ta + c0, w);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[g][(c0 >> 1) + i] = w[i];
+                } else if (c0 < half) {
+                    float w[4];
+                    tmem_ld_16x256b_x1(ta + c0, w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[g][(c0 >> 1) + i] = w[i];
+                }
             }
+        }
+        fp.mark(20);
+        tmem_ld_wait();
+        fp.mark(21);
+        const int mi = lane >> 3, r = lane & 7;    // lane j supplies the row address of matrix j/8, row j%8
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int fb = t * 128 + 32 * q + 16 * g;          // first feature of the group
+            const float b0 = bias[fb + (lane >> 2)], b8 = bias[fb + 8 + (lane >> 2)];
+            const float sc = (fb < nscale) ? qscale : 1.f;
+            const int f8 = fb + (mi & 1) * 8;
+            const uint32_t abase = yb_u32 + (uint32_t)((f8 >> 6) * kbb + (((f8 & 63) >> 3) << 4));
+#pragma unroll
+            for (int c0 = 0; c0 < HMAX; c0 += 16) {
+                if (c0 < half) {
+                    const bool full = (c0 + 16 <= HMAX) && (c0 + 16 <= half);
+                    uint32_t m[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < 2 || c0 + 16 <= HMAX) {
+                            const float bi = (j & 1) ? b8 : b0;
+                            float x0 = (v[g][(c0 >> 1) + 2 * j] + bi) * sc, x1 = (v[g][(c0 >> 1) + 2 * j + 1] + bi) * sc;
+                            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                            m[j] = pack_h2(x0, x1);
+                        } else {
+                            m[j] = 0u;
+                        }
+                    }
+                    const int tok = t0 + c0 + (full ? (mi >> 1) * 8 : 0) + r;
+                    const uint32_t addr = abase + (uint32_t)(tok * 128) ;
+                    const uint32_t swz = (uint32_t)((tok & 7) << 4);
+                    if (full) stsm_x4_t(addr ^ swz, m[0], m[1], m[2], m[3]);
+                    else stsm_x2_t(addr ^ swz, m[0], m[1]);
+                }
+            }
+        }
+    }
+    // QKV-style GEMM: every tile goes through the fp16 epilogue
+    template <int HMAX>
+    __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int kbb, int ntok, const float* bias, float qscale,
+                                             int nscale, unsigned char* yb) {
+        for (int t = 0; t < op.ntile; ++t) {
+            acc_wait(t);
+            epi_tile_h16<HMAX>(t, (uint32_t)(t * ntok), ntok, bias, false, qscale, nscale, yb, kbb);
         }
         tcgen05_fence_before();
     }
+    template <class Pre, class Epi>
+    __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int ntok, Pre pre, Epi epi) {
+        for (int t = 0; t < op.ntile; ++t) {
+            acc_wait(t);
+            epi_tile(t, (uint32_t)(t * ntok), ntok, pre, epi);   // overlaps the MMAs of tile t+1
+        }
+        tcgen05_fence_before();
+    }
+    template <int HMAX>
+    __device__ __forceinline__ void ffn(const FfnArgs& a) {
+        const int nt = a.fcw >> 7, dt = a.d >> 7;
+        if (!a.first) {       // the previous chunk's W2 MMAs must have read the hidden tile before it is overwritten
+            mbar_wait_warp(&bars[RU_BAR_CHUNK], chunkpar & 1u, lane);
+            chunkpar ^= 1u;
+        }
+        unsigned char* yb = a.yb;
+        const int kbb = a.kbb;
+        for (int t = 0; t < nt; ++t) {
+            acc_wait(t);
+            epi_tile_h16<HMAX>(t, (uint32_t)(t * a.Lp), a.Lp, a.b1 + a.f0, true, 1.f, 0, yb, kbb);
+            fp.mark(22);
+            tcgen05_fence_before();
+            fp.mark(23);
+            fence_proxy_async();                     // hidden k-blocks 2t, 2t+1 -> tensor-core reads
+            fp.mark(24);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[RU_BAR_RDY + t]);
+            fp.mark(3);
+        }
+        if (a.last) {
+            acc_wait(RU_ACC2);
+            float* h = a.h;
+            const int d = a.d + RU_HPAD;
+            for (int t2 = 0; t2 < dt; ++t2)
+                epi_tile(t2, a.acc2_col + (uint32_t)(t2 * a.Lp), a.Lp,
+                         [&](int f) { return a.b2[f]; },
+                         [&](int f, int t8, const float (&v)[8], float bi) {
+                             float* hf = h + t8 * d + f;   // d: padded row stride
+#pragma unroll
+                             for (int i = 0; i < 8; ++i) hf[i * d] += v[i] + bi;
+                         });
+            tcgen05_fence_before();
+        }
+    }
     __device__ __forceinline__ void sync() {
-        if (!(dbg & 16)) fence_proxy_async();   // operand tiles written by these threads -> tensor-core reads
+        fence_proxy_async();   // operand tiles written by these threads -> tensor-core reads
         named_bar_sync(1, RU_SYNC_THREADS);
     }
 };
 
 template <int DMODEL, int DH, int NKB, class Role>
 __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float* h, unsigned char* xb,
-                                              unsigned char* yb, float* par, int tid, int warp, int lane) {
+                                              unsigned char* yb, float* par, uint64_t* bars, int tid, int warp, int lane) {
     const int K = p.K, Ds = p.Ds, F = p.F, FC = p.fc;
     const int LpMax = (p.lmax + 15) & ~15;
     const int kbb = LpMax * 128;                       // bytes between 64-wide k blocks of X / Y
@@ -161,23 +386,21 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
     const float sm_scale_log2 = rsqrtf((float)DH) * 1.4426950408889634f;
     auto addr_s = [=](int r, int c) { return swz_off(r, c, kbb); };
     const int PF = p.par_floats;
+    // per-layer parameter block (biases + LayerNorm affine, packed by sfb_rollout_prepare): one bulk copy
     auto load_params = [&](int layer, int buf) {
-        const ROLayer& ly = p.layer[layer];
-        float* dst = par + (size_t)buf * PF;
-        const float* srcs[8] = {ly.bqkv, ly.bo, ly.b1, ly.b2, ly.ln1w, ly.ln1b, ly.ln2w, ly.ln2b};
-        const int lens[8] = {3 * DMODEL, DMODEL, F, DMODEL, DMODEL, DMODEL, DMODEL, DMODEL};
-        int off = 0;
-        for (int sgm = 0; sgm < 8; ++sgm) {
-            for (int i = tid * 4; i < lens[sgm]; i += RO_THREADS * 4) cp_async16(dst + off + i, srcs[sgm] + i);
-            off += lens[sgm];
+        if (Role::kCompute && tid == 0) {
+            mbar_arrive_expect_tx(&bars[RU_BAR_PAR + buf], (uint32_t)PF * 4u);
+            bulk_g2s(par + (size_t)buf * PF, p.par_g + (size_t)layer * PF, (uint32_t)PF * 4u, &bars[RU_BAR_PAR + buf],
+                     l2_policy_evict_last());
         }
-        cp_async_commit();
     };
     int pidx_prof = 0;
     const bool do_prof = Role::kCompute && (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
     auto stamp = [&]() { if (do_prof && pidx_prof < p.prof_cap) p.prof[pidx_prof++] = globaltimer_ns(); };
     uint32_t lcount = 0;
-    if (Role::kCompute) { load_params(0, 0); cp_async_wait_all(); }
+    const int my_clips = ((int)blockIdx.x < p.B) ? (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t total_layers = (uint32_t)my_clips * p.pred_len * p.layers;
+    load_params(0, 0);
     R.sync();
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -188,7 +411,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
             int L, base, pe0;
             if (p.mode == 0) { L = p.hist_tokens; base = step * K; pe0 = 0; }
             else { L = total < p.cond_tokens ? total : p.cond_tokens; base = total - L; pe0 = p.pe_tokens - L; }
-            const int Lp = (L + 15) & ~15, nmb = Lp >> 4, nkb = Lp >> 3;
+            const int Lp = (L + 15) & ~15, nmb = Lp >> 4, nkb = (L + 7) >> 3;   // key blocks holding a valid key
 
             stamp();   // 0 step start
             if (Role::kCompute) {
@@ -215,7 +438,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
 #pragma unroll
                            for (int i = 0; i < 8; ++i) {
                                const int t = t8 + i;
-                               h[t * DMODEL + f] = (t < L) ? v[i] + bi + __ldg(p.pe + (size_t)(pe0 + t) * DMODEL + f) : 0.f;
+                               h[t * (DMODEL + RU_HPAD) + f] = (t < L) ? v[i] + bi + __ldg(p.pe + (size_t)(pe0 + t) * DMODEL + f) : 0.f;
                            }
                        });
             }
@@ -224,11 +447,9 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
 
             for (int layer = 0; layer < p.layers; ++layer) {
                 const ROLayer& ly = p.layer[layer];
-                const float* pb = par + (size_t)(p.par_double ? (lcount & 1) : 0) * PF;
-                if (!p.par_double && lcount > 0) {
-                    if (Role::kCompute) { load_params(layer, 0); cp_async_wait_all(); }
-                    R.sync();
-                }
+                R.fp.enable(step == 1 && layer == 1);
+                R.fp.mark(9);
+                const float* pb = par + (size_t)(lcount & 1) * PF;
                 const float* s_bqkv = pb;
                 const float* s_bo = pb + 3 * DMODEL;
                 const float* s_b1 = pb + 4 * DMODEL;
@@ -238,90 +459,72 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 const float* l2w = l1w + 2 * DMODEL;
                 const float* l2b = l1w + 3 * DMODEL;
                 if (Role::kCompute) {
-                    if (p.par_double) load_params((layer + 1) % p.layers, (lcount + 1) & 1);
-                    if (!(p.dbg & 64)) ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
+                    // next layer's parameters: its buffer was last read before the barrier that ended the previous layer
+                    if (lcount + 1 < total_layers) load_params((layer + 1) % p.layers, (lcount + 1) & 1);
+                    mbar_wait_warp(&bars[RU_BAR_PAR + (lcount & 1)], (lcount >> 1) & 1u, lane);
+                    if (!(p.dbg & 64)) ln_to_half_q<DMODEL, RU_HPAD>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
                 }
                 R.sync();
                 stamp();   // LN1
-                // ---- packed q | k | v projection -> Y[token][3d] ----
+                R.fp.mark(11);
+                // ---- packed q | k | v projection -> Y[token][3d]; q pre-scaled by log2(e)/sqrt(dh) ----
                 {
                     const UOp op{ly.wqkv, DMODEL >> 6, 0, (3 * DMODEL) >> 7, 0, DMODEL >> 6};
-                    R.gemm(op, x_u32, kbb, Lp,
-                           [&](int f) { return s_bqkv[f]; },
-                           [&](int f, int t8, const float (&v)[8], float bi) {
-                               unsigned char* yf = yb + (f >> 6) * kbb + t8 * 128 + (f & 7) * 2;
-                               const int chunk = (f & 63) >> 3;
-#pragma unroll
-                               for (int i = 0; i < 8; ++i)
-                                   *reinterpret_cast<__half*>(yf + i * 128 + ((chunk ^ i) << 4)) = __float2half_rn(v[i] + bi);
-                           });
+                    R.template gemm_h16<NKB * 4>(op, x_u32, kbb, Lp, s_bqkv, sm_scale_log2, DMODEL, yb);
                 }
                 R.sync();
                 stamp();   // qkv
+                R.fp.mark(12);
                 if (Role::kCompute && !(p.dbg & 32)) {
                     if (NKB <= 6) {
                         for (int hh = warp; hh < p.heads; hh += RO_WARPS)
                             attn_head<DH, (NKB <= 6 ? NKB : 2), (NKB <= 6 ? NKB / 2 : 1)>(
-                                yb, addr_s, nmb, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb, sm_scale_log2, lane);
+                                yb, addr_s, nmb, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb, 1.f, lane);
                     } else {
                         for (int item = warp; item < p.heads * nmb; item += RO_WARPS) {
                             const int hh = item / nmb, mb = item % nmb;
                             attn_block<DH, NKB>(yb, addr_s, mb, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb,
-                                                sm_scale_log2, lane);
+                                                1.f, lane);
                         }
                     }
                 }
                 R.sync();
                 stamp();   // attn
+                R.fp.mark(13);
                 // ---- h += O Wo^T + bo ----
                 {
                     const UOp op{ly.wo, DMODEL >> 6, 0, DMODEL >> 7, 0, DMODEL >> 6};
                     R.gemm(op, y_u32, kbb, Lp,
                            [&](int f) { return s_bo[f]; },
                            [&](int f, int t8, const float (&v)[8], float bi) {
-                               float* hf = h + t8 * DMODEL + f;
+                               float* hf = h + t8 * (DMODEL + RU_HPAD) + f;
 #pragma unroll
-                               for (int i = 0; i < 8; ++i) hf[i * DMODEL] += v[i] + bi;
+                               for (int i = 0; i < 8; ++i) hf[i * (DMODEL + RU_HPAD)] += v[i] + bi;
                            });
                 }
                 R.sync();
                 stamp();   // outproj
+                R.fp.mark(14);
+                R.fp.mark(30);
                 if (Role::kCompute && !(p.dbg & 64))
-                    ln_to_half<DMODEL, (NKB < 6 ? NKB : 6)>(h, xb, addr_s, L, Lp, l2w, l2b, warp, lane);
+                    ln_to_half_q<DMODEL, RU_HPAD>(h, xb, addr_s, L, Lp, l2w, l2b, warp, lane);
+                R.fp.mark(31);
                 R.sync();
+                R.fp.mark(32);
                 stamp();   // LN2
-                // ---- h += W2 relu(W1 y + b1) + b2, FC hidden features at a time ----
+                R.fp.mark(15);
+                // ---- h += W2 relu(W1 y + b1) + b2: fused, the W2 MMAs of hidden tile t start as soon as its
+                //      epilogue has written the tile; FC hidden features per chunk ----
                 for (int f0 = 0; f0 < F; f0 += FC) {
                     const int fcw = (F - f0) < FC ? (F - f0) : FC;
-                    {
-                        const UOp op{ly.w1, DMODEL >> 6, f0 >> 7, fcw >> 7, 0, DMODEL >> 6};
-                        R.gemm(op, x_u32, kbb, Lp,
-                               [&](int f) { return s_b1[f0 + f]; },
-                               [&](int f, int t8, const float (&v)[8], float bi) {
-                               unsigned char* yf = yb + (f >> 6) * kbb + t8 * 128 + (f & 7) * 2;
-                               const int chunk = (f & 63) >> 3;
-#pragma unroll
-                               for (int i = 0; i < 8; ++i)
-                                   *reinterpret_cast<__half*>(yf + i * 128 + ((chunk ^ i) << 4)) = __float2half_rn(fmaxf(v[i] + bi, 0.f));
-                           });
-                    }
-                    R.sync();
-                    stamp();   // ffn1
-                    const bool first = (f0 == 0);
-                    {
-                        const UOp op{ly.w2, F >> 6, 0, DMODEL >> 7, f0 >> 6, fcw >> 6};
-                        R.gemm(op, y_u32, kbb, Lp,
-                               [&](int f) { return first ? s_b2[f] : 0.f; },
-                               [&](int f, int t8, const float (&v)[8], float bi) {
-                               float* hf = h + t8 * DMODEL + f;
-#pragma unroll
-                               for (int i = 0; i < 8; ++i) hf[i * DMODEL] += v[i] + bi;
-                           });
-                    }
-                    if (Role::kCompute && p.par_double && f0 + FC >= F) cp_async_wait_all();
-                    R.sync();
-                    stamp();   // ffn2
+                    const FfnArgs fa{ly.w1, ly.w2, s_b1, s_b2, DMODEL, F, f0, fcw, Lp, kbb, x_u32, y_u32, yb, h,
+                                     (uint32_t)((FC >> 7) * LpMax), f0 == 0, f0 + FC >= F};
+                    R.template ffn<NKB * 4>(fa);
                 }
+                R.sync();
+                stamp();   // ffn
+                R.fp.mark(10);
+                R.fp.enable(false);
                 ++lcount;
             }
 
@@ -329,7 +532,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
             if (Role::kCompute) {
                 for (int i = tid; i < 16 * DMODEL; i += RO_THREADS) {
                     const int r = i / DMODEL, c = i % DMODEL;
-                    *reinterpret_cast<__half*>(xb + addr_s(r, c)) = __float2half_rn(r < K ? h[(L - K + r) * DMODEL + c] : 0.f);
+                    *reinterpret_cast<__half*>(xb + addr_s(r, c)) = __float2half_rn(r < K ? h[(L - K + r) * (DMODEL + RU_HPAD) + c] : 0.f);
                 }
             }
             R.sync();
@@ -357,14 +560,17 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ro_umma_forward_kernel(const RO
     float* h = reinterpret_cast<float*>(smem + p.off_h);
     float* par = reinterpret_cast<float*>(smem + p.off_par);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
-    uint64_t* accfull = bars + 16;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
-    BRing ring{smem + p.off_ring, bars, bars + 8, p.nstage};
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + RU_BAR_TMEM);
+    BRing ring{smem + p.off_ring, bars + RU_BAR_FULL, bars + RU_BAR_EMPTY, p.nstage, p.stage_tiles};
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < p.nstage; ++s) { mbar_init(&ring.full[s], 1); mbar_init(&ring.empty[s], 1); }
-        mbar_init(accfull, 1);
+        for (int i = 0; i < 9; ++i) mbar_init(&bars[RU_BAR_ACC + i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&bars[RU_BAR_RDY + i], RO_WARPS);
+        mbar_init(&bars[RU_BAR_CHUNK], 1);
+        mbar_init(&bars[RU_BAR_PAR], 1);
+        mbar_init(&bars[RU_BAR_PAR + 1], 1);
         fence_mbar_init();
     }
     if (warp == RO_WARPS + 1) tmem_alloc(tmem_ptr, 512);
@@ -372,18 +578,25 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ro_umma_forward_kernel(const RO
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    const bool fine = p.prof != nullptr && p.prof_cap >= 5120 && blockIdx.x == 0;
 
-    if (warp == RO_WARPS) {
-        if (lane == 0) {
-            BProducer P{ring, 0u, l2_policy_evict_last(), p.dbg};
-            run_rollout_b<DMODEL, DH, NKB>(P, p, h, xb, yb, par, tid, warp, lane);
+    // register reallocation between the roles: each setmaxnreg sits inside its role's branch so that the
+    // allocator sees separate budgets (at a merge point it would take the smaller one for both)
+    if (warp >= RO_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(RU_REGS_SERVICE));
+        if (warp == RO_WARPS) {
+            if (lane == 0) {
+                BProducer P{ring, 0u, l2_policy_evict_last(), p.dbg, FineProf{fine ? p.prof + 2048 : nullptr, 0, 1024, false}};
+                run_rollout_b<DMODEL, DH, NKB>(P, p, h, xb, yb, par, bars, tid, warp, lane);
+            }
+        } else if (warp == RO_WARPS + 1) {
+            BMma M{ring, 0u, tmem, bars, 0u, lane, p.dbg, FineProf{(fine && lane == 0) ? p.prof + 3072 : nullptr, 0, 1024, false}};
+            run_rollout_b<DMODEL, DH, NKB>(M, p, h, xb, yb, par, bars, tid, warp, lane);
         }
-    } else if (warp == RO_WARPS + 1) {
-        BMma M{ring, 0u, tmem, accfull, lane, p.dbg};
-        run_rollout_b<DMODEL, DH, NKB>(M, p, h, xb, yb, par, tid, warp, lane);
     } else {
-        BCompute C{tmem, accfull, 0u, warp, lane, p.dbg};
-        run_rollout_b<DMODEL, DH, NKB>(C, p, h, xb, yb, par, tid, warp, lane);
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(RU_REGS_COMPUTE));
+        BCompute C{tmem, bars, 0u, 0u, warp, lane, p.dbg, FineProf{(fine && tid == 0) ? p.prof + 4096 : nullptr, 0, 1024, false}};
+        run_rollout_b<DMODEL, DH, NKB>(C, p, h, xb, yb, par, bars, tid, warp, lane);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -404,33 +617,36 @@ int ro_umma_plan(ROParams* p, int smem_limit, size_t* smem_bytes) {
     const int Lp = (p->lmax + 15) & ~15;
     const int wa = (d > Ds ? d : Ds);
     int wy = 3 * d;
-    int fc = F < 768 ? F : 768;
-    fc = fc / 128 * 128;
+    const int nchunk = (F + 767) / 768;
+    int fc = ((F + nchunk - 1) / nchunk + 127) / 128 * 128;     // hidden features per FFN chunk
     if (fc > wy) wy = fc;
-    if ((wy / 128) * Lp > 512) return -1;              // TMEM columns
+    if ((3 * d / 128) * Lp > 512 || (fc / 128 + d / 128) * Lp > 512) return -1;   // TMEM columns
+    if (fc / 128 > 8 || 3 * d / 128 > 8) return -1;                                  // accumulator barriers
     p->par_floats = 9 * d + F;
     const size_t x_bytes = (size_t)(wa / 64) * Lp * 128;
     const size_t y_bytes = (size_t)(wy / 64) * Lp * 128;
-    const size_t h_bytes = (size_t)Lp * d * 4;
-    for (int par_double = 1; par_double >= 0; --par_double) {
-        const size_t par_bytes = (size_t)(par_double ? 2 : 1) * p->par_floats * 4;
-        size_t off = 0;
-        p->off_a = (uint32_t)off; off += x_bytes;
-        p->off_b = (uint32_t)off; off += y_bytes;
-        p->off_h = (uint32_t)off; off += h_bytes;
-        p->off_par = (uint32_t)off; off += par_bytes;
-        p->off_bars = (uint32_t)off; off += 20 * 8;
-        off = (off + 1023) / 1024 * 1024;
-        if ((size_t)smem_limit < off + 2 * (size_t)RU_STAGE_BYTES) continue;
-        int nstage = (int)(((size_t)smem_limit - off) / RU_STAGE_BYTES);
-        if (nstage > 6) nstage = 6;
-        p->off_ring = (uint32_t)off;
-        p->nstage = nstage; p->par_double = par_double; p->hg = p->heads; p->fc = fc;
-        p->lda = 0; p->ldb = 0;
-        *smem_bytes = off + (size_t)nstage * RU_STAGE_BYTES;
-        return 0;
-    }
-    return -1;
+    const size_t h_bytes = (size_t)Lp * (d + RU_HPAD) * 4;
+    const size_t par_bytes = (size_t)2 * p->par_floats * 4;
+    size_t off = 0;
+    p->off_a = (uint32_t)off; off += x_bytes;
+    p->off_b = (uint32_t)off; off += y_bytes;
+    p->off_h = (uint32_t)off; off += h_bytes;
+    p->off_par = (uint32_t)off; off += par_bytes;
+    p->off_bars = (uint32_t)off; off += RU_BAR_WORDS * 8;
+    off = (off + 1023) / 1024 * 1024;
+    // 32 KB stages (two k-adjacent tiles) halve the per-stage handshakes; 16 KB stages when room is short
+    int stage_tiles = 2;
+    if ((size_t)smem_limit < off + 3 * (size_t)stage_tiles * RU_TILE_BYTES) stage_tiles = 1;
+    const size_t stage_bytes = (size_t)stage_tiles * RU_TILE_BYTES;
+    if ((size_t)smem_limit < off + 3 * stage_bytes) return -1;
+    int nstage = (int)(((size_t)smem_limit - off) / stage_bytes);
+    if (nstage > 8) nstage = 8;
+    p->stage_tiles = stage_tiles;
+    p->off_ring = (uint32_t)off;
+    p->nstage = nstage; p->par_double = 1; p->hg = p->heads; p->fc = fc;
+    p->lda = 0; p->ldb = 0;
+    *smem_bytes = off + (size_t)nstage * stage_bytes;
+    return 0;
 }
 
 template <int DMODEL, int DH, int NKB>
