@@ -257,27 +257,45 @@ def run_ours(args):
         sync_all()
 
         # ---------------- device-resident timing ----------------
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        # (1) serial: one batch at a time on one stream (per-batch latency; kernel durations with every SM)
         sa_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
                   torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        sampler = ClockSampler(local)
-        sampler.start()
-        n0 = engine.launch_count()
         sync_all()
-        ev[0].record()
         for i in range(args.steps):
             sa_ev[i][0].record()
             slots = sa(feats, init)
             sa_ev[i][1].record()
             ro(slots.view(B, T_in, K, D), T_out)
             sa_ev[i][2].record()
+        torch.cuda.synchronize(dev)
+        serial_sa_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in sa_ev]))
+        serial_ro_ms = float(np.mean([b.elapsed_time(c) for _, b, c in sa_ev]))
+        serial_ms = float(sa_ev[0][0].elapsed_time(sa_ev[-1][2])) / args.steps
+
+        # (2) the timed region: K batches through the two-stage pipeline (Slot Attention of batch i+1
+        #     overlaps the rollout of batch i on a second stream; same kernels, same per-batch results)
+        pipe = engine.HotPathPipeline(sa, ro, dev, clips=B)
+        with pipe:
+            for _ in range(max(3, args.warmup)):
+                pipe.submit(feats, init, B, T_in, T_out)
+        sync_all()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        timing = []
+        sampler = ClockSampler(local)
+        sampler.start()
+        n0 = engine.launch_count()
+        sync_all()
+        ev[0].record()
+        with pipe:
+            for i in range(args.steps):
+                pipe.submit(feats, init, B, T_in, T_out, timing=timing)
         ev[1].record()
         torch.cuda.synchronize(dev)
         launches = engine.launch_count() - n0
         clocks = sampler.result()
         ms_total = ev[0].elapsed_time(ev[1])
-        sa_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in sa_ev]))
-        ro_ms = float(np.mean([b.elapsed_time(c) for _, b, c in sa_ev]))
+        sa_ms = float(np.mean([t[0].elapsed_time(t[1]) for t in timing]))
+        ro_ms = float(np.mean([t[2].elapsed_time(t[3]) for t in timing]))
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -286,47 +304,74 @@ def run_ours(args):
         value = world * frames_per_step() / (ms_per_step * 1e-3)
 
         # ---------------- end-to-end with host buffers ----------------
+        # Same pipeline fed from pinned HOST buffers: every step copies its feature grids + initial slots
+        # host->device (8 chunks, Slot Attention starts on a chunk as soon as it has landed) and reads the
+        # extracted + predicted slots back; two steps in flight (double-buffered device staging).
         e2e = None
         if not args.no_e2e:
             h_feats = torch.empty((frames, N, C), dtype=torch.float32, pin_memory=True)
             h_feats.copy_(feats)
             h_init = torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True)
             h_init.copy_(init)
-            h_slots = torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True)
-            h_pred = torch.empty((B, T_out, K, D), dtype=torch.float32, pin_memory=True)
-            d_feats = torch.empty_like(feats)
-            d_init = torch.empty_like(init)
-            d_slots = torch.empty_like(init)
+            h_slots = [torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            h_pred = [torch.empty((B, T_out, K, D), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            d_feats = [torch.empty_like(feats) for _ in range(2)]
+            d_init = [torch.empty_like(init) for _ in range(2)]
+            d_slots = [torch.empty_like(init) for _ in range(2)]
             copy_stream = torch.cuda.Stream(dev)
+            out_stream = torch.cuda.Stream(dev)
             nchunk = 8
             cf = frames // nchunk
+            done_ev = [None, None]
 
-            def e2e_step():
-                main = torch.cuda.current_stream(dev)
-                copy_stream.wait_stream(main)
+            def e2e_submit(i):
+                sl = i & 1
+                if done_ev[sl] is not None:
+                    done_ev[sl].synchronize()            # staging buffers of step i-2 are free again
                 evs = []
                 with torch.cuda.stream(copy_stream):
-                    d_init.copy_(h_init, non_blocking=True)
+                    d_init[sl].copy_(h_init, non_blocking=True)
                     for c in range(nchunk):
-                        d_feats[c * cf:(c + 1) * cf].copy_(h_feats[c * cf:(c + 1) * cf], non_blocking=True)
+                        d_feats[sl][c * cf:(c + 1) * cf].copy_(h_feats[c * cf:(c + 1) * cf], non_blocking=True)
                         e = torch.cuda.Event()
                         e.record(copy_stream)
                         evs.append(e)
-                for c in range(nchunk):
-                    main.wait_event(evs[c])
-                    d_slots[c * cf:(c + 1) * cf] = sa(d_feats[c * cf:(c + 1) * cf], d_init[c * cf:(c + 1) * cf])
-                pred = ro(d_slots.view(B, T_in, K, D), T_out)
-                h_slots.copy_(d_slots, non_blocking=True)
-                h_pred.copy_(pred, non_blocking=True)
+                with torch.cuda.stream(pipe.s_sa):
+                    for c in range(nchunk):
+                        pipe.s_sa.wait_event(evs[c])
+                        d_slots[sl][c * cf:(c + 1) * cf] = sa(d_feats[sl][c * cf:(c + 1) * cf],
+                                                              d_init[sl][c * cf:(c + 1) * cf])
+                    ready = torch.cuda.Event()
+                    ready.record(pipe.s_sa)
+                pipe.s_ro.wait_event(ready)
+                with torch.cuda.stream(pipe.s_ro):
+                    pred = ro(d_slots[sl].view(B, T_in, K, D), T_out)
+                    rdone = torch.cuda.Event()
+                    rdone.record(pipe.s_ro)
+                pred.record_stream(out_stream)
+                out_stream.wait_event(rdone)
+                with torch.cuda.stream(out_stream):
+                    h_slots[sl].copy_(d_slots[sl], non_blocking=True)
+                    h_pred[sl].copy_(pred, non_blocking=True)
+                    fin = torch.cuda.Event()
+                    fin.record(out_stream)
+                done_ev[sl] = fin
+
+            def e2e_run(n):
+                with pipe:
+                    for i in range(n):
+                        e2e_submit(i)
+                    for e in done_ev:
+                        if e is not None:
+                            e.synchronize()
                 torch.cuda.synchronize(dev)
 
             e2e_steps = max(3, min(args.steps, 10))
-            for _ in range(2):
-                e2e_step()
+            e2e_run(2)
             sync_all()
+            done_ev = [None, None]
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
+            e2e_run(e2e_steps)
             dt = (time.perf_counter() - t0) / e2e_steps
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             if world > 1:
@@ -334,9 +379,10 @@ def run_ours(args):
             dt = float(tt.item())
             e2e = {'value': world * frames_per_step() / dt, 'unit': UNIT,
                    'h2d_bytes_per_step': int(h_feats.numel() * 4 + h_init.numel() * 4),
-                   'd2h_bytes_per_step': int(h_slots.numel() * 4 + h_pred.numel() * 4),
+                   'd2h_bytes_per_step': int(h_slots[0].numel() * 4 + h_pred[0].numel() * 4),
                    'ms_per_step': dt * 1e3, 'steps': e2e_steps,
-                   'note': f'pinned host buffers, {nchunk}-chunk H2D overlapped with Slot Attention'}
+                   'note': f'pinned host buffers, {nchunk}-chunk H2D overlapped with Slot Attention, '
+                           'two steps in flight (PCIe-bound: 806 MB host->device per step)'}
 
     if rank != 0:
         if world > 1:
@@ -353,7 +399,10 @@ def run_ours(args):
         'config': {'workload': WORKLOAD,
                    'arithmetic': 'fp16 tensor-core operands, fp32 accumulate / LayerNorm / softmax / GRU',
                    'l2': 'no flush needed: each step streams 805 MB of features (> 126 MB L2)',
-                   'per_gpu_clips': B, 'parallelism': f'clip-sharded x{world}, no data-path collective'},
+                   'per_gpu_clips': B, 'parallelism': f'clip-sharded x{world}, no data-path collective',
+                   'pipeline': 'two-stage over consecutive batches: Slot Attention of batch i+1 (84 SMs) runs '
+                               'concurrently with the rollout of batch i (one SM per clip); per-batch results unchanged',
+                   'serial_ms_per_step': serial_ms, 'serial_sa_ms': serial_sa_ms, 'serial_rollout_ms': serial_ro_ms},
         'clocks': clocks, 'gpu_launches': int(launches),
         'roofline': {'kernel': 'sfb_sa_forward: sa_prep + sa_update x3 + sa_pass<first> + sa_pass<next>',
                      'bound': 'hbm', 'achieved': sa_gbs, 'peak': pk['hbm'],

@@ -52,6 +52,12 @@ const char* sfb_strerror(int code);
 /* number of kernel launches this process has made through the library (bench.py's gpu_launches) */
 long long sfb_launch_count(void);
 
+/* Caps the grid of the persistent Slot Attention passes at `max_ctas` CTAs (0 = one per SM, the default).
+ * Process-wide.  Used when Slot Attention of the next clip batch runs concurrently with the rollout of the
+ * previous one (slotformer_b200.engine.HotPathPipeline): the rollout holds one SM per clip, Slot Attention is
+ * HBM-bound and keeps its bandwidth on the remaining SMs. */
+int sfb_sa_set_cta_limit(int max_ctas);
+
 /* Debug / profiling aids (not part of the operator surface).
  * sfb_debug_set_profile: device buffer of `capacity` uint64 that the NEXT forward calls fill with
  * %globaltimer stamps at phase boundaries (cluster 0 / CTA 0); pass NULL to switch it off.

@@ -11,6 +11,7 @@
 namespace {
 
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_sa_cta_limit{0};     // 0 = every SM; see sfb_sa_set_cta_limit
 unsigned long long* g_prof = nullptr;   // debug timeline buffer (device), see sfb_debug_set_profile
 int g_prof_cap = 0;
 
@@ -58,6 +59,12 @@ void sfb_debug_set_profile(void* device_buf, int capacity) {
 
 
 long long sfb_launch_count(void) { return g_launches.load(); }
+
+int sfb_sa_set_cta_limit(int max_ctas) {
+    if (max_ctas < 0) return SFB_E_BAD_SHAPE;
+    g_sa_cta_limit.store(max_ctas);
+    return SFB_OK;
+}
 
 const char* sfb_strerror(int code) {
     switch (code) {
@@ -148,6 +155,8 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     if (rc) return rc;
     if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
 
+    // persistent streaming passes: one CTA per SM, or fewer when the caller shares the GPU with the rollout
+    { const int lim = g_sa_cta_limit.load(); if (lim > 0 && lim < di.sms) di.sms = lim; }
     const int chunk = sa_pick_chunk(B, N, C, n_iter, chunk_frames);
     sfb::SAWorkspace ws;
     sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);

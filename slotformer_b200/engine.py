@@ -68,6 +68,8 @@ def load():
     lib.sfb_strerror.restype = c.c_char_p
     lib.sfb_strerror.argtypes = [c.c_int]
     lib.sfb_launch_count.restype = c.c_longlong
+    lib.sfb_sa_set_cta_limit.restype = c.c_int
+    lib.sfb_sa_set_cta_limit.argtypes = [c.c_int]
     lib.sfb_debug_set_profile.restype = None
     lib.sfb_debug_set_profile.argtypes = [c.c_void_p, c.c_int]
     lib.sfb_debug_umma_gemm.restype = c.c_int
@@ -99,7 +101,7 @@ def load():
 
 def exported_symbols():
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
-    return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_debug_set_profile',
+    return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_set_cta_limit', 'sfb_debug_set_profile',
             'sfb_debug_umma_gemm', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
             'sfb_rollout_forward']
@@ -122,6 +124,72 @@ def umma_gemm(W, X):
 
 def launch_count():
     return int(load().sfb_launch_count())
+
+
+def set_sa_cta_limit(max_ctas):
+    """Cap the grid of the persistent Slot Attention passes (0 = one CTA per SM)."""
+    _check(load().sfb_sa_set_cta_limit(int(max_ctas)))
+
+
+class HotPathPipeline:
+    """Two-stage software pipeline over consecutive clip batches.
+
+    Slot Attention of batch i+1 (HBM-bound, persistent CTAs) and the rollout of batch i (latency-bound, one
+    CTA per clip) use different resources, so they run concurrently on two streams: the rollout keeps
+    ``clips`` SMs, Slot Attention is capped at the remaining ones.  ``submit`` returns at once; the returned
+    event completes when that batch's predicted slots are ready.  Results are identical to calling the two
+    modules back to back (same kernels, same order per batch).
+    """
+
+    def __init__(self, slot_attention, rollouter, device, clips):
+        self.sa, self.ro, self.device = slot_attention, rollouter, torch.device(device)
+        self.s_sa = torch.cuda.Stream(self.device)
+        self.s_ro = torch.cuda.Stream(self.device)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.sa_ctas = sms - clips if 0 < clips <= sms // 2 else 0     # 0: no partition, plain stream order
+
+    def __enter__(self):
+        set_sa_cta_limit(self.sa_ctas)
+        cur = torch.cuda.current_stream(self.device)
+        self.s_sa.wait_stream(cur)
+        self.s_ro.wait_stream(cur)
+        return self
+
+    def __exit__(self, *exc):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.s_sa)
+        cur.wait_stream(self.s_ro)
+        set_sa_cta_limit(0)
+        return False
+
+    def submit(self, feats, init_slots, clips, frames_per_clip, pred_len, after=None, timing=None):
+        """feats [clips*frames_per_clip, N, C], init_slots [.., K, D] -> (slots, pred, done_event).
+
+        ``after``: optional event the Slot Attention stage waits for (e.g. the H2D copy of this batch).
+        ``timing``: optional list; receives (sa_start, sa_end, ro_start, ro_end) timing events."""
+        tm = timing is not None
+        with torch.cuda.stream(self.s_sa):
+            if after is not None:
+                self.s_sa.wait_event(after)
+            if tm:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(self.s_sa)
+            slots = self.sa(feats, init_slots)
+            ready = torch.cuda.Event(enable_timing=tm)
+            ready.record(self.s_sa)
+        slots.record_stream(self.s_ro)
+        self.s_ro.wait_event(ready)
+        with torch.cuda.stream(self.s_ro):
+            if tm:
+                e2 = torch.cuda.Event(enable_timing=True)
+                e2.record(self.s_ro)
+            K, D = slots.shape[1], slots.shape[2]
+            pred = self.ro(slots.view(clips, frames_per_clip, K, D), pred_len)
+            done = torch.cuda.Event(enable_timing=tm)
+            done.record(self.s_ro)
+        if tm:
+            timing.append((e0, ready, e2, done))
+        return slots, pred, done
 
 
 def _check(code):

@@ -189,3 +189,32 @@ def test_empty_batch():
     with torch.no_grad():
         out = m(torch.zeros((0, 256, 128), device=DEV), torch.zeros((0, 4, 128), device=DEV))
     assert out.shape == (0, 4, 128)
+
+
+def test_hot_path_pipeline_matches_serial_calls():
+    """Two-stream pipeline (Slot Attention of batch i+1 concurrent with the rollout of batch i, SM-limited
+    passes): bit-identical to calling the two modules back to back, for several batches in flight."""
+    from slotformer_b200 import engine
+    c, w, _, _ = cases.sa_case('sa_cfg2')
+    sa = sa_module(c, w, DEV, mask=False)
+    rc, rw, _ = cases.ro_case('ro_cfg2')
+    g = golden('ro_cfg2')
+    ro = ro_module(rc, rw, DEV, enc_t_pe=g['enc_t_pe'])
+    B, T, K, D, N, C = 16, 6, 6, 128, 4096, 128
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    batches = [(torch.randn((B * T, N, C), device=DEV, generator=gen), torch.randn((B * T, K, D), device=DEV, generator=gen))
+               for _ in range(3)]
+    with torch.no_grad():
+        ref = []
+        for f, s0 in batches:
+            s = sa(f, s0)
+            ref.append((s, ro(s.view(B, T, K, D), 10)))
+        torch.cuda.synchronize()
+        pipe = engine.HotPathPipeline(sa, ro, DEV, clips=B)
+        outs = []
+        with pipe:
+            for f, s0 in batches:
+                outs.append(pipe.submit(f, s0, B, T, 10))
+        torch.cuda.synchronize()
+    for (s, p, _), (rs, rp) in zip(outs, ref):
+        assert torch.equal(s, rs) and torch.equal(p, rp)
