@@ -173,6 +173,25 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
                         int T_h, int K, int Ds, int d, int F, int heads, int pred_len, int mode,
                         int cond_len, const void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Decoder epilogue (next row f2): the tail of StoSAVi.decode + postproc_mask   */
+/* ------------------------------------------------------------------------- */
+/* Everything after the deconvolution stack of the spatial-broadcast decoder (base_slots/models/savi.py:519-523):
+ *   dec_out        [B, K, 4, HW] fp32   decoder output, planes 0..2 = colour, plane 3 = mask logit
+ *   masks          [B, K, HW]    fp32   softmax over the K slots of plane 3
+ *   recon_combined [B, 3, HW]    fp32   sum_k colour_k * masks_k
+ *   seg            NULL, or [B, HW] int64: postproc_mask (video_prediction/vp_utils.py:20-41) of `masks` --
+ *                  the frame's background slot (smallest per-slot maximum) takes every pixel whose best score is
+ *                  below fg_thre, then argmax over slots (first maximum, as torch.argmax)
+ *   slot_max_ws    B*K uint32 of scratch, required iff seg != NULL
+ * Supported: 1 <= K <= 12, HW % 4 == 0, B <= 65535. */
+int sfb_decode_combine(const float* dec_out, float* masks, float* recon_combined, long long* seg,
+                       void* slot_max_ws, int B, int K, int HW, float fg_thre, void* stream);
+
+/* postproc_mask on given masks [B, K, HW] (vp_utils.py:20-41) -> seg [B, HW] int64.  K <= 16, B*K <= 65535. */
+int sfb_postproc_mask(const float* masks, long long* seg, void* slot_max_ws, int B, int K, int HW, float fg_thre,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,3 +226,33 @@ def rollout(hist, weights, pred_len, num_heads, num_layers, mode='slide',
         else:
             in_x = np.concatenate([in_x, pred], axis=1)        # single_step :88
     return np.stack(out, axis=1)                                        # :126
+
+
+# --------------------------------------------------------------------------------------------
+# decoder epilogue
+# --------------------------------------------------------------------------------------------
+def decode_combine(dec_out, dtype=np.float64):
+    """Tail of reference StoSAVi.decode (base_slots/models/savi.py:519-523).
+
+    dec_out [B, K, 4, H, W] -> (recon_combined [B,3,H,W], masks [B,K,1,H,W]):
+    masks = softmax over the slot axis of channel 3, recon_combined = sum_k dec_out[:, k, :3] * masks[:, k]."""
+    x = np.asarray(dec_out, dtype=dtype)
+    logit = x[:, :, 3:4]
+    e = np.exp(logit - logit.max(axis=1, keepdims=True))
+    masks = e / e.sum(axis=1, keepdims=True)
+    return (x[:, :, :3] * masks).sum(axis=1), masks
+
+
+def postproc_mask(batch_masks, fg_thre=0.5):
+    """Reference postproc_mask (video_prediction/vp_utils.py:20-41), index arithmetic -> bit exact.
+
+    batch_masks [B, T, N, 1, H, W] -> [B, T, H, W] int64.  np.argmin / np.argmax return the first
+    extremum, as torch.argmin / torch.argmax do."""
+    m = np.array(batch_masks, copy=True)
+    B, T, N, _, H, W = m.shape
+    m = m.reshape(B * T, N, H * W)
+    bg_idx = m.max(-1).argmin(-1)                       # vp_utils.py:32-33
+    bg_mask = m.max(1) < fg_thre                        # vp_utils.py:34-35
+    for f in range(B * T):                              # vp_utils.py:36-39
+        m[f, bg_idx[f], bg_mask[f]] = 1.
+    return m.argmax(1).reshape(B, T, H, W).astype(np.int64)

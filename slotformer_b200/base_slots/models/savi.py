@@ -50,6 +50,12 @@ def broadcast_decode(owner, slots):
     H, W = owner.resolution
     x = slots.reshape(bs * num_slots, slot_size, 1, 1).repeat(1, 1, *owner.dec_resolution)
     x = owner.decoder(owner.decoder_pos_embedding(x)).view(bs, num_slots, 4, H, W)
+    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad) \
+            and num_slots <= 12 and (H * W) % 4 == 0:
+        # inference on the GPU: softmax over slots + recombination in one streaming kernel (csrc/decode_combine.cu)
+        from ...engine import decode_combine
+        recon_combined, masks = decode_combine(x)
+        return recon_combined, x[:, :, :3], masks, slots
     recons, masks = x[:, :, :3], F.softmax(x[:, :, 3:], dim=1)
     return (recons * masks).sum(dim=1), recons, masks, slots
 

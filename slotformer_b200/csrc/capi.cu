@@ -3,6 +3,7 @@
 #include "../../include/sfb200.h"
 #include "sa_kernel.h"
 #include "ro_kernel.h"
+#include "decode_kernel.h"
 
 #include <atomic>
 #include <cstring>
@@ -341,6 +342,58 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     }
     if (e != cudaSuccess) return cuda_err(e);
     g_launches.fetch_add(1);
+    return SFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decoder epilogue (section 8 f2)
+// ------------------------------------------------------------------------------------------
+int sfb_decode_combine(const float* dec_out, float* masks, float* recon_combined, long long* seg,
+                       void* slot_max_ws, int B, int K, int HW, float fg_thre, void* stream) {
+    if (B == 0) return SFB_OK;
+    if (!dec_out || !masks || !recon_combined) return SFB_E_NULL;
+    if (seg && !slot_max_ws) return SFB_E_NULL;
+    if (B < 0 || K < 1 || K > 12 || HW < 4 || (HW & 3)) return SFB_E_BAD_SHAPE;
+    if (B > 65535) return SFB_E_BAD_SHAPE;
+    if (!aligned16(dec_out) || !aligned16(masks) || !aligned16(recon_combined)) return SFB_E_BAD_ALIGN;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* smax = seg ? reinterpret_cast<unsigned int*>(slot_max_ws) : nullptr;
+    cudaError_t e;
+    if (smax) {
+        e = cudaMemsetAsync(smax, 0, (size_t)B * K * sizeof(unsigned int), st);
+        if (e != cudaSuccess) return cuda_err(e);
+    }
+    e = sfb::decode_combine_launch(dec_out, masks, recon_combined, smax, B, K, HW, di.sms, st);
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
+    if (seg) {
+        e = sfb::seg_argmax_launch(masks, smax, seg, B, K, HW, fg_thre, di.sms, st);
+        if (e != cudaSuccess) return cuda_err(e);
+        g_launches.fetch_add(1);
+    }
+    return SFB_OK;
+}
+
+int sfb_postproc_mask(const float* masks, long long* seg, void* slot_max_ws, int B, int K, int HW, float fg_thre,
+                      void* stream) {
+    if (B == 0) return SFB_OK;
+    if (!masks || !seg || !slot_max_ws) return SFB_E_NULL;
+    if (B < 0 || B > 65535 || K < 1 || K > 16 || HW < 1 || (long long)B * K > 65535) return SFB_E_BAD_SHAPE;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* smax = reinterpret_cast<unsigned int*>(slot_max_ws);
+    cudaError_t e = cudaMemsetAsync(smax, 0, (size_t)B * K * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return cuda_err(e);
+    if ((e = sfb::mask_max_launch(masks, smax, B * K, HW, di.sms, st)) != cudaSuccess) return cuda_err(e);
+    if ((e = sfb::seg_argmax_launch(masks, smax, seg, B, K, HW, fg_thre, di.sms, st)) != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(2);
     return SFB_OK;
 }
 

@@ -74,7 +74,9 @@ struct PassCfg {
     static_assert(SMEM <= 232448, "pass kernel: shared memory budget");
 };
 
-template <int C, bool FIRST, int EIN>
+// XS (first pass, K == 8 only): sum_n t[n] is accumulated explicitly.  With K <= 7 the otherwise idle 8th
+// slot column of the probability operand is set to 1, so the aggregation MMAs deliver sum_n t[n] for free.
+template <int C, bool FIRST, int EIN, bool XS>
 __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SAPassParams p) {
     using Cfg = PassCfg<C, FIRST, EIN>;
     constexpr int PASS_WARPS = Cfg::NW, PASS_THREADS = PASS_WARPS * 32;
@@ -208,12 +210,13 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
                         for (int i = lane; i < (16 - nvalid) * (C * EIN / 16); i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         __syncwarp();
                     }
+                    {
+                        // all 16 raw rows are loaded before anything is stored back (the fp16 t rows alias the
+                        // raw rows), so the four row groups are independent and their latencies overlap
+                        f32x2 v[4][C / 16];
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        f32x2 v[2][C / 16];
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int row = 8 * hf + 4 * rr + pxi;
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int row = 4 * rr + pxi;
                             const unsigned char* tp = stg + (size_t)(row * C + 4 * ch8) * EIN;
 #pragma unroll
                             for (int i = 0; i < C / 32; ++i) {
@@ -228,32 +231,39 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
                             }
                         }
                         __syncwarp();
+                        // one sweep: sum and sum of squares together (one shuffle phase instead of two), then
+                        // t = x * rstd - mu * rstd as a single fused multiply-add per pair
+                        float sm[4], sq[4];
 #pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int row = 8 * hf + 4 * rr + pxi;
-                            f32x2 s2 = v[rr][0];
+                        for (int rr = 0; rr < 4; ++rr) {
+                            f32x2 s2 = v[rr][0], q2 = mul2(v[rr][0], v[rr][0]);
 #pragma unroll
-                            for (int i = 1; i < C / 16; ++i) s2 = add2(s2, v[rr][i]);
-                            float sm = lo2(s2) + hi2(s2);
-                            sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-                            sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-                            sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-                            const float nmu = -sm * (1.f / C);
-                            const f32x2 nmu2 = pack2(nmu, nmu);
-                            f32x2 q2 = pack2(0.f, 0.f);
+                            for (int i = 1; i < C / 16; ++i) { s2 = add2(s2, v[rr][i]); q2 = fma2(v[rr][i], v[rr][i], q2); }
+                            sm[rr] = lo2(s2) + hi2(s2);
+                            sq[rr] = lo2(q2) + hi2(q2);
+                        }
 #pragma unroll
-                            for (int i = 0; i < C / 16; ++i) { v[rr][i] = add2(v[rr][i], nmu2); q2 = fma2(v[rr][i], v[rr][i], q2); }
-                            float qv = lo2(q2) + hi2(q2);
-                            qv += __shfl_xor_sync(0xffffffffu, qv, 1);
-                            qv += __shfl_xor_sync(0xffffffffu, qv, 2);
-                            qv += __shfl_xor_sync(0xffffffffu, qv, 4);
-                            const float rstd = rsqrtf(qv * (1.f / C) + LN_EPS);
+                        for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], o);
+                                sq[rr] += __shfl_xor_sync(0xffffffffu, sq[rr], o);
+                            }
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int row = 4 * rr + pxi;
+                            const float mu = sm[rr] * (1.f / C);
+                            const float var = fmaxf(fmaf(-mu, mu, sq[rr] * (1.f / C)), 0.f);
+                            const float rstd = rsqrtf(var + LN_EPS);
                             const f32x2 r2 = pack2(rstd, rstd);
+                            const float nb = -mu * rstd;
+                            const f32x2 nb2 = pack2(nb, nb);
                             unsigned char* rowp = stg + row * ROWB + (ch8 & 1) * 8;
 #pragma unroll
                             for (int i = 0; i < C / 32; ++i) {
-                                const f32x2 t0 = mul2(v[rr][2 * i], r2), t1 = mul2(v[rr][2 * i + 1], r2);
-                                xs2[2 * i] = add2(xs2[2 * i], t0); xs2[2 * i + 1] = add2(xs2[2 * i + 1], t1);
+                                const f32x2 t0 = fma2(v[rr][2 * i], r2, nb2), t1 = fma2(v[rr][2 * i + 1], r2, nb2);
+                                if (XS) { xs2[2 * i] = add2(xs2[2 * i], t0); xs2[2 * i + 1] = add2(xs2[2 * i + 1], t1); }
                                 const int chk = ((ch8 >> 1) + 4 * i) ^ (row & 7);
                                 uint2 pk; pk.x = pack_h2(lo2(t0), hi2(t0)); pk.y = pack_h2(lo2(t1), hi2(t1));
                                 *reinterpret_cast<uint2*>(rowp + chk * 16) = pk;
@@ -324,6 +334,7 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
                         if (s1ok) mk[(size_t)(2 * t4 + 1) * N + pxb] = pb1;
                     }
                 }
+                if (FIRST && !XS && t4 == 3) { pa1 = 1.f / SA_PSCALE; pb1 = 1.f / SA_PSCALE; }   // slot column 7 := 1
                 const __half2 ha = __floats2half2_rn(pa0 * SA_PSCALE, pa1 * SA_PSCALE);
                 const __half2 hb = __floats2half2_rn(pb0 * SA_PSCALE, pb1 * SA_PSCALE);
                 {
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
         cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
         cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
         if (lane < 4) { colsum_w[warp * 8 + 2 * lane] = cs0; colsum_w[warp * 8 + 2 * lane + 1] = cs1; }
-        if (FIRST) {
+        if (FIRST && XS) {
             float xs[C / 32][4];
 #pragma unroll
             for (int i = 0; i < C / 32; ++i) {
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
                         const int c = 16 * cb + g + 8 * (e >> 1);
                         const int slot = 2 * t4 + (e & 1);
                         part[slot * C + c] = uacc[cb][e];
+                        if (FIRST && !XS && slot == 7) part[8 * C + 8 + c] = uacc[cb][e];   // sum_n t[n][c]
                     }
             } else if (warp == 1 && lane < 8) {
                 float a = 0.f;
@@ -444,16 +456,22 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
     }
 }
 
-template <int C, bool FIRST, int EIN>
-static cudaError_t pass_launch_t(const SAPassParams& p, int sms, cudaStream_t st) {
+template <int C, bool FIRST, int EIN, bool XS>
+static cudaError_t pass_launch_x(const SAPassParams& p, int sms, cudaStream_t st) {
     using Cfg = PassCfg<C, FIRST, EIN>;
-    auto kern = sa_pass_kernel<C, FIRST, EIN>;
+    auto kern = sa_pass_kernel<C, FIRST, EIN, XS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
     const int items = p.nframes * p.nchunk;
     const int grid = items < sms ? items : sms;
     kern<<<grid, Cfg::NW * 32, Cfg::SMEM, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int C, bool FIRST, int EIN>
+static cudaError_t pass_launch_t(const SAPassParams& p, int sms, cudaStream_t st) {
+    if (FIRST && p.K == 8) return pass_launch_x<C, FIRST, EIN, true>(p, sms, st);
+    return pass_launch_x<C, FIRST, EIN, false>(p, sms, st);
 }
 
 cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, int smem_limit, cudaStream_t st) {

@@ -95,6 +95,12 @@ def load():
         c.c_void_p, c.c_void_p, c.POINTER(_ROWeights), c.c_int, c.c_int, c.c_int, c.c_int,
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t,
         c.c_void_p]
+    lib.sfb_decode_combine.restype = c.c_int
+    lib.sfb_decode_combine.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
+                                       c.c_int, c.c_float, c.c_void_p]
+    lib.sfb_postproc_mask.restype = c.c_int
+    lib.sfb_postproc_mask.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_float,
+                                      c.c_void_p]
     _lib = lib
     return lib
 
@@ -104,7 +110,7 @@ def exported_symbols():
     return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_set_cta_limit', 'sfb_debug_set_profile',
             'sfb_debug_umma_gemm', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
-            'sfb_rollout_forward']
+            'sfb_rollout_forward', 'sfb_decode_combine', 'sfb_postproc_mask']
 
 
 def umma_gemm(W, X):
@@ -351,3 +357,51 @@ class RolloutEngine:
                 int(cond_len or 0), self._ws.data_ptr(), ws_bytes, _stream(dev))
         _check(rc)
         return out
+
+
+# --------------------------------------------------------------------------- #
+# Decoder epilogue
+# --------------------------------------------------------------------------- #
+FG_THRE = 0.5      # reference video_prediction/vp_utils.py:11
+
+
+def decode_combine(dec_out, want_seg=False, fg_thre=FG_THRE):
+    """Tail of StoSAVi.decode (reference savi.py:519-523) as one streaming kernel.
+
+    dec_out [B, K, 4, H, W] f32 (deconv output) -> (recon_combined [B,3,H,W], masks [B,K,1,H,W]) and, with
+    ``want_seg``, the post-processed segmentation [B,H,W] int64 (reference postproc_mask)."""
+    lib = load()
+    _require_cuda_f32('dec_out', dec_out)
+    if dec_out.dim() != 5 or dec_out.shape[2] != 4:
+        raise SfbError(f'dec_out must be [B, K, 4, H, W], got {tuple(dec_out.shape)}')
+    dec_out = dec_out.contiguous()
+    B, K, _, H, W = dec_out.shape
+    dev = dec_out.device
+    masks = torch.empty((B, K, 1, H, W), dtype=torch.float32, device=dev)
+    recon = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    seg = torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_seg else None
+    ws = torch.empty((max(B * K, 1),), dtype=torch.int32, device=dev) if want_seg else None
+    if B > 0:
+        with torch.cuda.device(dev):
+            _check(lib.sfb_decode_combine(dec_out.data_ptr(), masks.data_ptr(), recon.data_ptr(),
+                                          seg.data_ptr() if want_seg else None, ws.data_ptr() if want_seg else None,
+                                          B, K, H * W, float(fg_thre), _stream(dev)))
+    return (recon, masks, seg) if want_seg else (recon, masks)
+
+
+def postproc_mask(batch_masks, fg_thre=FG_THRE):
+    """Reference postproc_mask (vp_utils.py:20-41): batch_masks [B, T, N, 1, H, W] f32 -> [B, T, H, W] int64."""
+    lib = load()
+    _require_cuda_f32('batch_masks', batch_masks)
+    if batch_masks.dim() != 6 or batch_masks.shape[3] != 1:
+        raise SfbError(f'batch_masks must be [B, T, N, 1, H, W], got {tuple(batch_masks.shape)}')
+    B, T, N, _, H, W = batch_masks.shape
+    m = batch_masks.contiguous()
+    dev = m.device
+    seg = torch.empty((B, T, H, W), dtype=torch.int64, device=dev)
+    if B * T > 0:
+        ws = torch.empty((B * T * N,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _check(lib.sfb_postproc_mask(m.data_ptr(), seg.data_ptr(), ws.data_ptr(), B * T, N, H * W,
+                                         float(fg_thre), _stream(dev)))
+    return seg
