@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
 
     auto issue = [&](uint32_t n) {
         if (n < total_tiles && lane == 0) {
+            if (FIRST) bulk_wait_read<0>();      // the x^ store that sourced this stage has read it
             const int il = n / nbw, j = n % nbw;
             const int item = (int)blockIdx.x + il * (int)gridDim.x;
             const int fl = item / p.nchunk, c = item % p.nchunk;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
             nvalid = nvalid < 0 ? 0 : (nvalid > 16 ? 16 : nvalid);
             mbar_wait(&my_bars[s], (n / NST) & 1);
             if (nvalid > 0 && !(p.dbg & 4)) {
-                if (FIRST) {
+                if (FIRST && !(p.dbg & 8)) {
                     // ---- normalise 16 pixels in place: fp32 rows -> swizzled fp16 t = (x-mu)*rstd ----
                     // (the LayerNorm affine is folded into q~ and into the slot update; t rows 8h..8h+7
                     //  land on raw rows 4h..4h+3, which are already in registers)
@@ -272,14 +273,18 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
                     }
                     __syncwarp();
                     if (p.xhat != nullptr && !(p.dbg & 2)) {
-                        // ready-made smem image of the tile -> x^ ring in global memory
-                        uint4* dst = reinterpret_cast<uint4*>(
-                            p.xhat + ((size_t)(f % p.xhat_frames) * tiles_frame + tb) * (16 * C));
-                        const uint4* srcv = reinterpret_cast<const uint4*>(stg);
-#pragma unroll
-                        for (int q = 0; q < XT_BYTES / 512; ++q) dst[lane + 32 * q] = srcv[lane + 32 * q];
+                        // ready-made smem image of the tile -> x^ ring in global memory: one TMA bulk store issued by
+                        // lane 0 (no register round trip; the warp goes straight on to the tensor-core part)
+                        fence_proxy_async();          // the generic-proxy writes of t precede the async-proxy read
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_s2g(p.xhat + ((size_t)(f % p.xhat_frames) * tiles_frame + tb) * (16 * C), stg, XT_BYTES,
+                                     ring_fits_l2 ? l2_policy_evict_last() : l2_policy_evict_first());
+                            bulk_commit();
+                        }
                     }
                 }
+                if (p.dbg & 16) { __syncwarp(); continue; }      // (timing experiment: LayerNorm only)
                 const uint32_t tile_u32 = smem_u32(stg);
                 // ---- logits: 16 pixels x 8 slots, log2 domain (scale folded into q~) ----
                 // four independent accumulator chains (hi/lo x even/odd k-step): legacy HMMA has a long
@@ -454,6 +459,7 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
         }
         __syncthreads();
     }
+    if (FIRST && lane == 0) bulk_wait_read<0>();   // no x^ store may still be reading this CTA's shared memory
 }
 
 template <int C, bool FIRST, int EIN, bool XS>
