@@ -109,8 +109,6 @@ struct Consumer {
                         for (int ks = 0; ks < 4; ++ks)
                             ldsm_x4(bf[ks], pan + row * 128 + (((2 * ks + ((lane >> 3) & 1)) ^ (row & 7)) << 4));
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ring.empty[s]);     // panel is in registers
 #pragma unroll
                     for (int mb = 0; mb < NMB; ++mb) {
                         if (mb < nmb) {
@@ -126,6 +124,12 @@ struct Consumer {
                             }
                         }
                     }
+                    // The stage is released only after the panel fragments have been CONSUMED: an arrive issued right
+                    // after the ldmatrix instructions does not wait for their data, and the producer's next TMA fill
+                    // could overwrite the panel under a load still in flight (seen as rare, non-repeatable outputs
+                    // with the d = 256 shapes).
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ring.empty[s]);
                 }
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb) {

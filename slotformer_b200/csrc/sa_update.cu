@@ -137,8 +137,6 @@ struct UConsumer {
                     bl[2 * hf][0] = r4[0]; bl[2 * hf][1] = r4[1]; bl[2 * hf + 1][0] = r4[2]; bl[2 * hf + 1][1] = r4[3];
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.empty[s]);
 #pragma unroll
             for (int mb = 0; mb < NMB; ++mb) {
                 const int row = 16 * mb + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -156,6 +154,10 @@ struct UConsumer {
                     mma_f16(acc[mb], ah[ks], bl[ks][0], bl[ks][1]);
                 }
             }
+            // release the stage only once its fragments have been consumed by the MMAs above: an arrive issued right
+            // after the ldmatrix instructions would not wait for their data (see ro_kernel.cu)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[s]);
         }
     }
 };
