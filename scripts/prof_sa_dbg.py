@@ -14,7 +14,7 @@ feats = torch.randn((384, 4096, 128), device=dev); init = torch.randn((384, 6, 1
 with torch.no_grad():
     for lim in (0, 84):
         engine.set_sa_cta_limit(lim)
-        for dbg in (0, 2):
+        for dbg in (0,):
             os.environ['SFB_DBG'] = str(dbg)
             for _ in range(3): sa(feats, init)
             torch.cuda.synchronize()

@@ -26,9 +26,11 @@
 
 namespace sfb {
 
-// warps per CTA.  12 warps (3 per scheduler, 2-stage rings) were measured SLOWER than 8 warps with
-// 3-stage rings (481 vs 433 us per Slot Attention call): ring depth matters more than warp count.
-constexpr int pass_warps(int C) { return C == 128 ? 8 : 8; }
+// warps per CTA.  First pass: 8 (12 warps with 2-stage rings were measured SLOWER, 481 vs 433 us per Slot
+// Attention call: with 8 KB fp32 stages ring depth matters more than warp count, and the kernel needs ~240
+// registers).  Later passes stream 4 KB fp16 tiles and are bound by instruction latency (ncu: 35 % issue
+// slots used, "wait" + short-scoreboard stalls), so they run 12 warps (3 per scheduler) with 4-stage rings.
+constexpr int pass_warps(int C, bool first) { return (C == 128 && !first) ? 12 : 8; }
 static constexpr float SA_PSCALE = 1024.f;   // probabilities are stored as fp16(1024 * a)
 static constexpr float LN_EPS = 1e-5f;
 
@@ -54,12 +56,12 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 
 template <int C, bool FIRST, int EIN>
 struct PassCfg {
-    static constexpr int NW = pass_warps(C);
+    static constexpr int NW = pass_warps(C, FIRST);
     static constexpr int KS = C / 16;
     static constexpr int ROWB = C * 2;                       // x^ row bytes
     static constexpr int XT_BYTES = 16 * ROWB;               // x^ tile (16 px) bytes
     static constexpr int STAGE_BYTES = FIRST ? 16 * C * EIN : XT_BYTES;   // EIN = input element bytes (4 fp32, 2 bf16)
-    static constexpr int NST = (FIRST && EIN == 4) ? (C == 128 ? 3 : 2) : (C == 128 ? 6 : 4);
+    static constexpr int NST = (FIRST && EIN == 4) ? (C == 128 ? 3 : 2) : (C == 128 ? (FIRST ? 6 : 4) : 4);
     static constexpr int NQB = (C == 128) ? 2 : 1;           // q~ buffers (double-buffered if room)
     static constexpr int NREG = KS * 4;
     static constexpr int OFF_STAGES = 0;
@@ -77,7 +79,7 @@ struct PassCfg {
 // XS (first pass, K == 8 only): sum_n t[n] is accumulated explicitly.  With K <= 7 the otherwise idle 8th
 // slot column of the probability operand is set to 1, so the aggregation MMAs deliver sum_n t[n] for free.
 template <int C, bool FIRST, int EIN, bool XS>
-__global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SAPassParams p) {
+__global__ void __launch_bounds__(pass_warps(C, FIRST) * 32, 1) sa_pass_kernel(const SAPassParams p) {
     using Cfg = PassCfg<C, FIRST, EIN>;
     constexpr int PASS_WARPS = Cfg::NW, PASS_THREADS = PASS_WARPS * 32;
     constexpr int KS = Cfg::KS, ROWB = Cfg::ROWB, XT_BYTES = Cfg::XT_BYTES;
@@ -93,7 +95,8 @@ __global__ void __launch_bounds__(pass_warps(C) * 32, 1) sa_pass_kernel(const SA
 
     const int N = p.N, K = p.K;
     const int items = p.nframes * p.nchunk;
-    const int nbw = p.chunk_px / (16 * PASS_WARPS);  // 16-px tiles per warp per item
+    const int tiles_chunk0 = p.chunk_px >> 4;
+    const int nbw = (tiles_chunk0 - warp + PASS_WARPS - 1) / PASS_WARPS;  // 16-px tiles of this warp per item (warp w: tiles w, w+NW, ...)
     const int tiles_chunk = p.chunk_px >> 4;
     const int tiles_frame = p.nchunk * tiles_chunk;
     const int my_items = (items > (int)blockIdx.x) ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
