@@ -119,6 +119,13 @@ struct UConsumer {
     __device__ __forceinline__ void gemm(const __half*, int, int, int nkb, const __half* Ahi,
                                          const __half* Alo, int lda, float (&acc)[NMB][4]) {
         const uint32_t ah_u32 = smem_u32(Ahi), al_u32 = smem_u32(Alo);
+        // one accumulator per split term (hi*hi, lo*hi, hi*lo): three independent MMA chains per row block instead of
+        // one chain of 12 dependent MMAs per k block (legacy HMMA has a ~35-cycle dependent-issue latency)
+        float t3[NMB][3][4];
+#pragma unroll
+        for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) t3[mb][t][0] = t3[mb][t][1] = t3[mb][t][2] = t3[mb][t][3] = 0.f;
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb, ++pidx) {
             const int s = pidx % ring.nstage;
@@ -149,9 +156,9 @@ struct UConsumer {
                 }
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    mma_f16(acc[mb], ah[ks], bh[ks][0], bh[ks][1]);
-                    mma_f16(acc[mb], al[ks], bh[ks][0], bh[ks][1]);
-                    mma_f16(acc[mb], ah[ks], bl[ks][0], bl[ks][1]);
+                    mma_f16(t3[mb][0], ah[ks], bh[ks][0], bh[ks][1]);
+                    mma_f16(t3[mb][1], al[ks], bh[ks][0], bh[ks][1]);
+                    mma_f16(t3[mb][2], ah[ks], bl[ks][0], bl[ks][1]);
                 }
             }
             // release the stage only once its fragments have been consumed by the MMAs above: an arrive issued right
@@ -159,6 +166,10 @@ struct UConsumer {
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[s]);
         }
+#pragma unroll
+        for (int mb = 0; mb < NMB; ++mb)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mb][e] += (t3[mb][0][e] + t3[mb][1][e]) + t3[mb][2][e];
     }
 };
 
