@@ -550,9 +550,14 @@ static cudaError_t update_launch_t(const SAUpdateParams& p, cudaStream_t st) {
 }
 
 cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st) {
-    // 16*NMB rows per CTA: the most rows (fewest weight re-reads) that still gives every SM a CTA
-    const bool big = p.nframes >= 4 * sms;
-    if (C == 128) return big ? update_launch_t<128, 4>(p, st) : update_launch_t<128, 2>(p, st);
+    // 16*NMB rows (2*NMB frames) per CTA.  A CTA's time grows with NMB (41 us at 2, 69 us at 4), every CTA streams
+    // the whole weight set, so: the smallest NMB whose grid still fits one wave of the SMs this call may use.
+    if (C == 128) {
+        const int need = (p.nframes + sms - 1) / sms;             // frames per CTA for a single wave
+        if (need <= 4) return update_launch_t<128, 2>(p, st);
+        if (need <= 6) return update_launch_t<128, 3>(p, st);
+        return update_launch_t<128, 4>(p, st);
+    }
     return update_launch_t<192, 2>(p, st);
 }
 
