@@ -81,7 +81,8 @@ class RNNPredictorWrapper(Predictor):
             self._detach_state()
         out = self.base_predictor(x)
         shape = out.shape
-        self.rnn.flatten_parameters()
+        if not (out.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.rnn.flatten_parameters()       # (inside a CUDA-graph capture it would move the weights into the graph's pool)
         out, self.hidden_state = self.rnn(out.reshape(1, -1, shape[-1]), self.hidden_state)
         self.step += 1
         return self.out_projector(out[0]).view(shape)

@@ -184,10 +184,10 @@ class StoSAVi(BaseModel):
         x = self.encoder_pos_embedding(x).flatten(2, 3).permute(0, 2, 1).contiguous()
         return self.encoder_out_layer(x)
 
-    def encode(self, img, prev_slots=None):
-        """img [B, T, 3, H, W] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D], features)."""
-        B, T = img.shape[:2]
-        feats = self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
+    def _frame_loop(self, feats, prev_slots):
+        """The serial per-frame chain (reference savi.py:393-410): predictor -> kernel_dist_layer -> sample ->
+        Slot Attention, T times.  feats [B, T, N, C] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D])."""
+        B, T = feats.shape[:2]
         start = self.init_latents.repeat(B, 1, 1)
         dists, slots = [], []
         for t in range(T):                                  # frames are a serial chain
@@ -196,7 +196,99 @@ class StoSAVi(BaseModel):
             prev_slots = self.slot_attention(feats[:, t], self._sample_dist(dist))   # hot path 1
             dists.append(dist)
             slots.append(prev_slots)
-        return torch.stack(dists, dim=1), torch.stack(slots, dim=1), feats
+        return torch.stack(dists, dim=1), torch.stack(slots, dim=1)
+
+    # -- the frame loop as ONE CUDA-graph launch -------------------------------------
+    # Per frame the loop issues ~45 small launches (2-layer Transformer + LSTM predictor, the distribution head
+    # and the 5 Slot Attention kernels); at SAVi batch sizes that is launch-bound.  In inference the whole T-frame
+    # chain is captured once per (B, T, first-frame mode) and replayed: same kernels, same order, same results.
+    use_cuda_graph = True
+
+    def _graph_key(self, feats, prev_slots, has_state):
+        ver = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (tuple(feats.shape), feats.dtype, feats.device, prev_slots is not None, has_state, ver)
+
+    @staticmethod
+    def _state_tensors(state):
+        if state is None:
+            return None
+        return (state,) if isinstance(state, torch.Tensor) else tuple(state)
+
+    def _frame_loop_graphed(self, feats, prev_slots):
+        # the recurrent state of the predictor is Python-side module state: it enters the captured loop through
+        # static buffers and leaves it through the captured final-state tensors
+        pred = self.predictor
+        stateful = hasattr(pred, 'hidden_state')
+        h_in = self._state_tensors(pred.hidden_state) if stateful else None
+        single = stateful and isinstance(pred.hidden_state, torch.Tensor)
+        if hasattr(pred, 'rnn'):
+            pred.rnn.flatten_parameters()                   # before the key: flattening re-points the weights once
+        key = self._graph_key(feats, prev_slots, h_in is not None)
+        cache = self.__dict__.setdefault('_loop_graphs', {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 4:
+                cache.clear()                               # weights changed or many shapes: start over
+            s_feats = torch.empty_like(feats)
+            s_prev = torch.empty_like(prev_slots) if prev_slots is not None else None
+            s_h = tuple(torch.empty_like(h) for h in h_in) if h_in is not None else None
+            s_feats.copy_(feats)
+            if s_prev is not None:
+                s_prev.copy_(prev_slots)
+            if s_h is not None:
+                for d, h in zip(s_h, h_in):
+                    d.copy_(h)
+            step0 = pred.step if stateful else 0
+
+            def run():
+                if stateful:
+                    pred.hidden_state = None if s_h is None else (s_h[0] if single else s_h)
+                    pred.step = step0
+                out = self._frame_loop(s_feats, s_prev)
+                return out, (self._state_tensors(pred.hidden_state) if stateful else None)
+
+            side = torch.cuda.Stream(feats.device)
+            side.wait_stream(torch.cuda.current_stream(feats.device))
+            with torch.cuda.stream(side):                   # warm-up outside the capture (lazy handles, workspaces)
+                run()
+            torch.cuda.current_stream(feats.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out, h_out = run()
+            ent = cache[key] = (graph, s_feats, s_prev, s_h, out, h_out, (pred.step - step0) if stateful else 0)
+            if stateful:
+                pred.step = step0
+        graph, s_feats, s_prev, s_h, out, h_out, nsteps = ent
+        s_feats.copy_(feats)
+        if s_prev is not None:
+            s_prev.copy_(prev_slots)
+        if s_h is not None:
+            for d, h in zip(s_h, h_in):
+                d.copy_(h)
+        graph.replay()
+        if stateful:
+            if h_out is None:
+                pred.hidden_state = None
+            else:
+                new = tuple(h.clone() for h in h_out)
+                pred.hidden_state = new[0] if (len(new) == 1 and not isinstance(self.predictor.rnn, nn.LSTM)) else new
+            pred.step += nsteps
+        return out[0].clone(), out[1].clone()
+
+    def encode(self, img, prev_slots=None):
+        """img [B, T, 3, H, W] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D], features)."""
+        B, T = img.shape[:2]
+        feats = self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
+        if self.use_cuda_graph and feats.is_cuda and not torch.is_grad_enabled() and not self.training:
+            try:
+                dists, slots = self._frame_loop_graphed(feats.contiguous(), prev_slots)
+                return dists, slots, feats
+            except RuntimeError as e:                       # an op that cannot be captured: stay eager from now on
+                if 'captur' not in str(e).lower() and 'graph' not in str(e).lower():
+                    raise
+                self.use_cuda_graph = False
+        dists, slots = self._frame_loop(feats, prev_slots)
+        return dists, slots, feats
 
     def _reset_rnn(self):
         self.predictor.reset()

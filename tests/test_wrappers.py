@@ -136,3 +136,33 @@ def test_training_step_uses_autograd_path():
     x = torch.randn(2, 2, 3, 128, device='cuda', requires_grad=True)
     ro(x, 2).square().mean().backward()
     assert x.grad is not None and ro.in_proj.weight.grad is not None
+
+
+@pytest.mark.gpu
+def test_savi_frame_loop_cuda_graph_matches_eager():
+    """the per-frame chain (predictor -> distribution head -> Slot Attention) replayed as one
+    CUDA graph gives bit-identical slots to the eager loop, for the first clip (no previous slots) and for a
+    continuation (previous slots given), and is re-captured when a weight changes."""
+    from slotformer_b200.base_slots.models import StoSAVi
+    m = W.build_savi(StoSAVi).cuda()
+    img = torch.cat([W.savi_input()] * 2, dim=0).cuda()          # [4, 3, 3, 64, 64]
+    def both(x, graph):
+        """first clip (fresh recurrent state), then a continuation that carries slots AND the LSTM state over"""
+        m.use_cuda_graph = graph
+        m.predictor.reset()
+        d0, s0, _ = m.encode(x)
+        d1, s1, _ = m.encode(x, prev_slots=s0[:, -1])
+        return d0, s0, d1, s1
+
+    with torch.no_grad():
+        ref = both(img, False)
+        for _ in range(2):                                       # capture, then replay
+            got = both(img, True)
+            assert all(torch.equal(a, b) for a, b in zip(ref, got))
+        assert m.use_cuda_graph and len(m._loop_graphs) >= 2     # really went through the graphs
+        img2 = img.flip(0).contiguous()                          # new inputs through the captured graphs
+        assert all(torch.equal(a, b) for a, b in zip(both(img2, False), both(img2, True)))
+        m.slot_attention.project_q[1].weight.mul_(1.01)          # a changed weight invalidates the capture
+        new = both(img2, True)
+        assert all(torch.equal(a, b) for a, b in zip(both(img2, False), new))
+        assert not torch.equal(new[1], got[1])
