@@ -236,3 +236,19 @@ def test_rollout_mma_engine_matches_tcgen05_engine_and_repeats(monkeypatch):
         for _ in range(3):
             assert torch.equal(a, m(x, c['pred_len']))
     assert rel_max(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < 4e-3
+
+
+@pytest.mark.parametrize('K,N', [(8, 1000), (8, 4096), (7, 520), (1, 4096)])
+def test_slot_attention_slot_count_edges_vs_oracle(K, N):
+    """Slot counts around the probability operand's 8 columns at C = 128: K = 8 takes the explicit x-sum path, K = 7
+    puts the constant-one column right next to the last real slot, K = 1 leaves seven idle columns; ragged N."""
+    c = dict(B=3, N=N, C=128, D=128, Dm=256, K=K, iters=2, mask=True, seed=40 + K)
+    w = cases.make_sa_weights(c['C'], c['D'], c['Dm'], c['seed'])
+    feats, slots = cases.make_sa_inputs(c['B'], c['N'], c['C'], c['D'], c['K'], c['seed'])
+    feats = feats + 0.75          # a common offset: exercises the single-sweep variance (E[x^2] - mu^2)
+    ref, ref_mask = O.slot_attention(feats, slots, w, c['iters'], return_mask=True)
+    m = sa_module(c, w, DEV)
+    with torch.no_grad():
+        out, mask = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
+    assert rel_max(out.cpu().numpy(), ref) < 1e-3
+    assert np.abs(mask.cpu().numpy() - ref_mask).max() < 2e-3
