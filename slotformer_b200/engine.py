@@ -168,6 +168,29 @@ class HotPathPipeline:
         set_sa_cta_limit(0)
         return False
 
+    def capture(self, batches, clips, frames_per_clip, pred_len):
+        """Capture ``submit`` of every (feats, init_slots) pair in ``batches`` into ONE CUDA graph (both streams, with
+        their cross-stream dependencies), so that replaying it costs the host a single launch: the overlap of the two
+        stages no longer depends on the host staying ahead of the GPU.  Returns (graph, [(slots, pred), ...]); the
+        outputs are static tensors that every ``graph.replay()`` overwrites; inputs are read in place."""
+        dev = self.device
+        cap = torch.cuda.Stream(dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):                         # warm-up outside the capture
+            with self:
+                for f, s0 in batches[:2]:
+                    self.submit(f, s0, clips, frames_per_clip, pred_len)
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        outs = []
+        with torch.cuda.graph(graph, stream=cap):
+            with self:
+                for f, s0 in batches:
+                    sl, pr, _ = self.submit(f, s0, clips, frames_per_clip, pred_len)
+                    outs.append((sl, pr))
+        return graph, outs
+
     def submit(self, feats, init_slots, clips, frames_per_clip, pred_len, after=None, timing=None):
         """feats [clips*frames_per_clip, N, C], init_slots [.., K, D] -> (slots, pred, done_event).
 
@@ -183,7 +206,8 @@ class HotPathPipeline:
             slots = self.sa(feats, init_slots)
             ready = torch.cuda.Event(enable_timing=tm)
             ready.record(self.s_sa)
-        slots.record_stream(self.s_ro)
+        if not torch.cuda.is_current_stream_capturing():
+            slots.record_stream(self.s_ro)      # (a captured graph owns its memory pool; nothing to record there)
         self.s_ro.wait_event(ready)
         with torch.cuda.stream(self.s_ro):
             if tm:
