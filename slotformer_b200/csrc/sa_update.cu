@@ -108,6 +108,12 @@ struct UProducer {
     __device__ __forceinline__ void sync() {}
 };
 
+// split-precision terms of every slot-update GEMM: 3 = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-like),
+// 2 = without the activation-lo term (activations rounded to fp16 once, weights still hi + lo)
+#ifndef SA_UPD_TERMS
+#define SA_UPD_TERMS 3
+#endif
+
 template <int NMB>
 struct UConsumer {
     static constexpr bool kConsumer = true;
@@ -152,12 +158,16 @@ struct UConsumer {
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t off = (uint32_t)(row * lda + kb * 64 + 16 * ks + (lane >> 4) * 8) * 2u;
                     ldsm_x4(ah[ks], ah_u32 + off);
+#if SA_UPD_TERMS >= 3
                     ldsm_x4(al[ks], al_u32 + off);
+#endif
                 }
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     mma_f16(t3[mb][0], ah[ks], bh[ks][0], bh[ks][1]);
+#if SA_UPD_TERMS >= 3
                     mma_f16(t3[mb][1], al[ks], bh[ks][0], bh[ks][1]);
+#endif
                     mma_f16(t3[mb][2], ah[ks], bl[ks][0], bl[ks][1]);
                 }
             }
