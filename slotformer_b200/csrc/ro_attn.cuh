@@ -132,10 +132,10 @@ __device__ __forceinline__ void ln_to_half_v(const float* h, unsigned char* out,
 // different banks.  Four independent accumulators keep the per-lane sums off one dependent chain.
 template <int DMODEL, int HPAD, class Addr>
 __device__ __forceinline__ void ln_to_half_q(const float* h, unsigned char* out, Addr addr, int L, int Lp,
-                                             const float* gw, const float* gb, int warp, int lane) {
+                                             const float* gw, const float* gb, int warp, int lane, int rbegin = 0) {
     constexpr int NV = DMODEL / 16, HS = DMODEL + HPAD;
     const int j = lane & 3, rsub = lane >> 2;
-    for (int row0 = 0; row0 < Lp; row0 += RO_WARPS * 8) {
+    for (int row0 = rbegin; row0 < Lp; row0 += RO_WARPS * 8) {      // rows [rbegin, Lp)
         if (row0 + warp * 8 >= Lp) break;            // warp-uniform
         const int r = row0 + warp * 8 + rsub;
         const bool valid = r < L;
@@ -179,14 +179,25 @@ __device__ __forceinline__ void ln_to_half_q(const float* h, unsigned char* out,
 // One (head, 16-query block) of softmax(Q K^T / sqrt(dh)) V.  Q/K/V live in `buf` (fp16, stride
 // ldb) at column offsets qcol/kcol/vcol; the result overwrites the Q block it came from.
 template <int DH, int NKB, class Addr>
+__device__ __forceinline__ void attn_rows(unsigned char* buf, Addr addr, int qrow0, int qcol, int kcol,
+                                          int vcol, int L, int nkb, float sm_scale_log2, int lane);
+
+template <int DH, int NKB, class Addr>
 __device__ __forceinline__ void attn_block(unsigned char* buf, Addr addr, int mb, int qcol, int kcol,
                                            int vcol, int L, int nkb, float sm_scale_log2, int lane) {
+    attn_rows<DH, NKB>(buf, addr, 16 * mb, qcol, kcol, vcol, L, nkb, sm_scale_log2, lane);
+}
+
+// 16 query rows starting at qrow0 (any multiple of 8 that keeps the block inside the buffer)
+template <int DH, int NKB, class Addr>
+__device__ __forceinline__ void attn_rows(unsigned char* buf, Addr addr, int qrow0, int qcol, int kcol,
+                                          int vcol, int L, int nkb, float sm_scale_log2, int lane) {
     const int g = lane >> 2, t4 = lane & 3;
     const uint32_t b_u32 = smem_u32(buf);
     uint32_t qf[DH / 16][4];
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) {
-        const int row = 16 * mb + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int row = qrow0 + (lane & 7) + ((lane >> 3) & 1) * 8;
         ldsm_x4(qf[ks], b_u32 + addr(row, qcol + 16 * ks + (lane >> 4) * 8));
     }
     float s[NKB][4];
@@ -262,8 +273,8 @@ __device__ __forceinline__ void attn_block(unsigned char* buf, Addr addr, int mb
 #pragma unroll
     for (int nb = 0; nb < DH / 8; ++nb) {
         const int col = qcol + 8 * nb + 2 * t4;
-        *reinterpret_cast<__half2*>(buf + addr(16 * mb + g, col)) = __floats2half2_rn(o[nb][0] * i0, o[nb][1] * i0);
-        *reinterpret_cast<__half2*>(buf + addr(16 * mb + g + 8, col)) = __floats2half2_rn(o[nb][2] * i1, o[nb][3] * i1);
+        *reinterpret_cast<__half2*>(buf + addr(qrow0 + g, col)) = __floats2half2_rn(o[nb][0] * i0, o[nb][1] * i0);
+        *reinterpret_cast<__half2*>(buf + addr(qrow0 + g + 8, col)) = __floats2half2_rn(o[nb][2] * i1, o[nb][3] * i1);
     }
 }
 
@@ -272,7 +283,7 @@ __device__ __forceinline__ void attn_block(unsigned char* buf, Addr addr, int mb
 // is short (NMB * NKB accumulators fit in registers).
 template <int DH, int NKB, int NMB, class Addr>
 __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb, int qcol, int kcol, int vcol,
-                                          int L, int nkb, float sm_scale_log2, int lane) {
+                                          int L, int nkb, float sm_scale_log2, int lane, int qrow0 = 0) {
     const int g = lane >> 2, t4 = lane & 3;
     const uint32_t b_u32 = smem_u32(buf);
     uint32_t qf[NMB][DH / 16][4];
@@ -280,7 +291,7 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
     for (int mb = 0; mb < NMB; ++mb)
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks) {
-            const int row = 16 * (mb < nmb ? mb : 0) + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int row = qrow0 + 16 * (mb < nmb ? mb : 0) + (lane & 7) + ((lane >> 3) & 1) * 8;
             ldsm_x4(qf[mb][ks], b_u32 + addr(row, qcol + 16 * ks + (lane >> 4) * 8));
         }
     float s[NMB][NKB][4];
@@ -298,8 +309,10 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
                 ldsm_x4(kf, b_u32 + addr(row, kcol + 16 * ks + ((lane >> 3) & 1) * 8));
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb) {
-                    mma_f16(s[mb][nb], qf[mb][ks], kf[0], kf[1]);
-                    mma_f16(s[mb][nb + 1], qf[mb][ks], kf[2], kf[3]);
+                    if (mb < nmb) {                 // (warp-uniform) blocks beyond nmb are not computed at all
+                        mma_f16(s[mb][nb], qf[mb][ks], kf[0], kf[1]);
+                        mma_f16(s[mb][nb + 1], qf[mb][ks], kf[2], kf[3]);
+                    }
                 }
             }
         }
@@ -310,7 +323,7 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
         m0[mb] = -INFINITY; m1[mb] = -INFINITY;
 #pragma unroll
         for (int nb = 0; nb < NKB; ++nb) {
-            if (nb < nkb) {
+            if (nb < nkb && mb < nmb) {
                 if (8 * nb + 8 <= L) {        // block of valid keys only (warp-uniform): no masking work
 #pragma unroll
                     for (int e = 0; e < 4; ++e) s[mb][nb][e] *= sm_scale_log2;
@@ -339,7 +352,7 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
         l0[mb] = 0.f; l1[mb] = 0.f;
 #pragma unroll
         for (int nb = 0; nb < NKB; ++nb) {
-            if (nb < nkb) {
+            if (nb < nkb && mb < nmb) {
                 const float e0 = fast_exp2(s[mb][nb][0] - m0[mb]), e1 = fast_exp2(s[mb][nb][1] - m0[mb]);
                 const float e2 = fast_exp2(s[mb][nb][2] - m1[mb]), e3 = fast_exp2(s[mb][nb][3] - m1[mb]);
                 l0[mb] += e0 + e1; l1[mb] += e2 + e3;
@@ -372,9 +385,11 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
                 ldsm_x4_t(vf, b_u32 + addr(row, vcol + 8 * nb + (lane >> 4) * 8));
 #pragma unroll
                 for (int mb = 0; mb < NMB; ++mb) {
-                    const uint32_t a[4] = {pf[mb][2 * kk][0], pf[mb][2 * kk][1], pf[mb][2 * kk + 1][0], pf[mb][2 * kk + 1][1]};
-                    mma_f16(o_[mb][nb], a, vf[0], vf[1]);
-                    mma_f16(o_[mb][nb + 1], a, vf[2], vf[3]);
+                    if (mb < nmb) {
+                        const uint32_t a[4] = {pf[mb][2 * kk][0], pf[mb][2 * kk][1], pf[mb][2 * kk + 1][0], pf[mb][2 * kk + 1][1]};
+                        mma_f16(o_[mb][nb], a, vf[0], vf[1]);
+                        mma_f16(o_[mb][nb + 1], a, vf[2], vf[3]);
+                    }
                 }
             }
         }
@@ -387,8 +402,8 @@ __device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb
 #pragma unroll
             for (int nb = 0; nb < DH / 8; ++nb) {
                 const int col = qcol + 8 * nb + 2 * t4;
-                *reinterpret_cast<__half2*>(buf + addr(16 * mb + g, col)) = __floats2half2_rn(o_[mb][nb][0] * i0, o_[mb][nb][1] * i0);
-                *reinterpret_cast<__half2*>(buf + addr(16 * mb + g + 8, col)) = __floats2half2_rn(o_[mb][nb][2] * i1, o_[mb][nb][3] * i1);
+                *reinterpret_cast<__half2*>(buf + addr(qrow0 + 16 * mb + g, col)) = __floats2half2_rn(o_[mb][nb][0] * i0, o_[mb][nb][1] * i0);
+                *reinterpret_cast<__half2*>(buf + addr(qrow0 + 16 * mb + g + 8, col)) = __floats2half2_rn(o_[mb][nb][2] * i1, o_[mb][nb][3] * i1);
             }
         }
     }

@@ -27,8 +27,8 @@ static constexpr int RU_MAX_STAGE_TILES = 2;                // k-adjacent tiles 
 static constexpr int RU_TILE_HALVES = 8192;
 static constexpr int RU_SYNC_THREADS = RO_THREADS + 32;   // compute warps + MMA warp
 static constexpr int RU_THREADS = RO_THREADS + 128;   // + one warpgroup: TMA producer, MMA issuer, two idle warps
-static constexpr int RU_REGS_COMPUTE = 216;          // setmaxnreg: the epilogue / attention warps take what the
-static constexpr int RU_REGS_SERVICE = 72;           // service warpgroup gives up (8*32*216 + 4*32*72 = 64512)
+static constexpr int RU_REGS_COMPUTE = 224;          // setmaxnreg: the epilogue / attention warps take what the
+static constexpr int RU_REGS_SERVICE = 56;           // service warpgroup gives up (8*32*224 + 4*32*56 = 64512)
 
 struct UOp {
     const __half* base;   // packed matrix (ro_pack2 layout)
@@ -48,6 +48,10 @@ static constexpr int RU_BAR_TMEM = 36;    // TMEM base address slot
 static constexpr int RU_BAR_WORDS = 40;
 static constexpr int RU_ACC2 = 8;
 
+// extras of an fp16-epilogue GEMM call: absolute first feature of op tile 0 (bias / column index), first token row
+// of the N range, first accumulator barrier and first TMEM column to use
+struct H16Ext { int feat0, row0, tbase; uint32_t dcol0; };
+
 struct BRing {
     unsigned char* stages;
     uint64_t* full;
@@ -61,8 +65,9 @@ struct FfnArgs {
     const __half *w1, *w2;
     const float *b1, *b2;      // smem copies (b1 indexed by absolute hidden feature)
     int d, F, f0, fcw;         // model width, hidden width, chunk start / width
-    int Lp, kbb;
-    uint32_t x_u32, y_u32;
+    int Lp, kbb;               // tokens (MMA N) of this call, bytes between k blocks
+    int row0;                  // first token row of this call (last-layer pruning: only the tail rows)
+    uint32_t x_u32, y_u32;     // operand buffers at row 0
     unsigned char* yb;
     float* h;
     uint32_t acc2_col;         // TMEM column of the W2 accumulator
@@ -121,7 +126,7 @@ struct BProducer {
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) { emit(op); }
     template <int HMAX>
-    __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int, int, const float*, float, int, unsigned char*) { emit(op); }
+    __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int, int, const float*, float, int, unsigned char*, H16Ext) { emit(op); }
     // weight order of the fused FFN: every W1 tile of the chunk, then the W2 k-block pairs in tile order
     template <int HMAX>
     __device__ __forceinline__ void ffn(const FfnArgs& a) {
@@ -145,7 +150,7 @@ struct BMma {
     // MMAs of `op` into TMEM columns dcol + t * ntok (tile t); b_u32: smem address of the token operand's
     // k-block 0 of this op, kblock_bytes apart per 64 k.  acc_first: the first k-step accumulates too.
     __device__ __forceinline__ void issue(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, uint32_t dcol,
-                                          bool acc_first, bool commit_tiles) {
+                                          bool acc_first, bool commit_tiles, int tbase = 0) {
         const uint32_t idesc = umma_idesc_f16(128, ntok);
         for (int t = 0; t < op.ntile; ++t) {
             for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles, ++pidx) {
@@ -178,7 +183,7 @@ struct BMma {
                 __syncwarp();
                 fp.mark(3);
             }
-            if (commit_tiles) commit(&bars[RU_BAR_ACC + t]);   // this tile's accumulator is complete
+            if (commit_tiles) commit(&bars[RU_BAR_ACC + tbase + t]);   // this tile's accumulator is complete
         }
     }
     __device__ __forceinline__ void commit(uint64_t* bar) {
@@ -191,8 +196,8 @@ struct BMma {
     }
     template <int HMAX>
     __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, const float*, float,
-                                             int, unsigned char*) {
-        issue(op, b_u32, kblock_bytes, ntok, 0u, false, true);
+                                             int, unsigned char*, H16Ext x) {
+        issue(op, b_u32 + (uint32_t)(x.row0 * 128), kblock_bytes, ntok, x.dcol0, false, true, x.tbase);
     }
     __device__ __forceinline__ void ffn2_part(const FfnArgs& a, int j) {
         fp.mark(4);
@@ -200,7 +205,7 @@ struct BMma {
         fp.mark(5);
         rdypar ^= 1u << j;
         tcgen05_fence_after();
-        issue(UOp{a.w2, a.F >> 6, 0, a.d >> 7, (a.f0 >> 6) + 2 * j, 2}, a.y_u32 + (uint32_t)(2 * j * a.kbb), a.kbb, a.Lp,
+        issue(UOp{a.w2, a.F >> 6, 0, a.d >> 7, (a.f0 >> 6) + 2 * j, 2}, a.y_u32 + (uint32_t)(2 * j * a.kbb + a.row0 * 128), a.kbb, a.Lp,
               a.acc2_col, !(a.first && j == 0), false);
     }
     // all W1 tiles first (they only need x^), then each W2 k-block pair as soon as the epilogue warps have
@@ -208,7 +213,7 @@ struct BMma {
     template <int HMAX>
     __device__ __forceinline__ void ffn(const FfnArgs& a) {
         const int nt = a.fcw >> 7, kpd = a.d >> 6;
-        issue(UOp{a.w1, kpd, a.f0 >> 7, nt, 0, kpd}, a.x_u32, a.kbb, a.Lp, 0u, false, true);
+        issue(UOp{a.w1, kpd, a.f0 >> 7, nt, 0, kpd}, a.x_u32 + (uint32_t)(a.row0 * 128), a.kbb, a.Lp, 0u, false, true);
         for (int j = 0; j < nt; ++j) ffn2_part(a, j);
         commit(a.last ? &bars[RU_BAR_ACC + RU_ACC2] : &bars[RU_BAR_CHUNK]);
     }
@@ -257,7 +262,8 @@ struct BCompute {
     // 16-feature x 16-token block is one store instruction instead of 8 scattered 2-byte stores per thread.
     template <int HMAX>
     __device__ __forceinline__ void epi_tile_h16(int t, uint32_t dcol, int ntok, const float* bias, bool relu,
-                                                 float qscale, int nscale, unsigned char* yb, int kbb) {
+                                                 float qscale, int nscale, unsigned char* yb, int kbb, int feat0 = 0,
+                                                 int row0 = 0) {
         if (dbg & 4) return;
         const int q = warp & 3, half = ntok >> 1, t0 = (warp >> 2) * half;   // HMAX >= half: tokens per warp
         const uint32_t yb_u32 = smem_u32(yb);
@@ -286,7 +292,7 @@ struct BCompute {
         const int mi = lane >> 3, r = lane & 7;    // lane j supplies the row address of matrix j/8, row j%8
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const int fb = t * 128 + 32 * q + 16 * g;          // first feature of the group
+            const int fb = feat0 + t * 128 + 32 * q + 16 * g;  // first (absolute) feature of the group
             const float b0 = bias[fb + (lane >> 2)], b8 = bias[fb + 8 + (lane >> 2)];
             const float sc = (fb < nscale) ? qscale : 1.f;
             const int f8 = fb + (mi & 1) * 8;
@@ -307,7 +313,7 @@ struct BCompute {
                             m[j] = 0u;
                         }
                     }
-                    const int tok = t0 + c0 + (full ? (mi >> 1) * 8 : 0) + r;
+                    const int tok = row0 + t0 + c0 + (full ? (mi >> 1) * 8 : 0) + r;
                     const uint32_t addr = abase + (uint32_t)(tok * 128) ;
                     const uint32_t swz = (uint32_t)((tok & 7) << 4);
                     if (full) stsm_x4_t(addr ^ swz, m[0], m[1], m[2], m[3]);
@@ -319,10 +325,10 @@ struct BCompute {
     // QKV-style GEMM: every tile goes through the fp16 epilogue
     template <int HMAX>
     __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int kbb, int ntok, const float* bias, float qscale,
-                                             int nscale, unsigned char* yb) {
+                                             int nscale, unsigned char* yb, H16Ext x) {
         for (int t = 0; t < op.ntile; ++t) {
-            acc_wait(t);
-            epi_tile_h16<HMAX>(t, (uint32_t)(t * ntok), ntok, bias, false, qscale, nscale, yb, kbb);
+            acc_wait(x.tbase + t);
+            epi_tile_h16<HMAX>(t, x.dcol0 + (uint32_t)(t * ntok), ntok, bias, false, qscale, nscale, yb, kbb, x.feat0, x.row0);
         }
         tcgen05_fence_before();
     }
@@ -345,7 +351,7 @@ struct BCompute {
         const int kbb = a.kbb;
         for (int t = 0; t < nt; ++t) {
             acc_wait(t);
-            epi_tile_h16<HMAX>(t, (uint32_t)(t * a.Lp), a.Lp, a.b1 + a.f0, true, 1.f, 0, yb, kbb);
+            epi_tile_h16<HMAX>(t, (uint32_t)(t * a.Lp), a.Lp, a.b1 + a.f0, true, 1.f, 0, yb, kbb, 0, a.row0);
             fp.mark(22);
             tcgen05_fence_before();
             fp.mark(23);
@@ -363,7 +369,7 @@ struct BCompute {
                 epi_tile(t2, a.acc2_col + (uint32_t)(t2 * a.Lp), a.Lp,
                          [&](int f) { return a.b2[f]; },
                          [&](int f, int t8, const float (&v)[8], float bi) {
-                             float* hf = h + t8 * d + f;   // d: padded row stride
+                             float* hf = h + (a.row0 + t8) * d + f;   // d: padded row stride
 #pragma unroll
                              for (int i = 0; i < 8; ++i) hf[i * d] += v[i] + bi;
                          });
@@ -458,6 +464,17 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 const float* l1b = l1w + DMODEL;
                 const float* l2w = l1w + 2 * DMODEL;
                 const float* l2b = l1w + 3 * DMODEL;
+                // Last layer: only the last K tokens feed out_proj (slotformer.py:121), so queries, attention output,
+                // out-proj, LN2 and the feed-forward block are needed for those rows only; keys / values still for every
+                // token.  [rq0, rq0 + nq): the 16-aligned-size, 8-aligned-start row range that covers [L - K, L).
+                int rq0 = 0, nq = Lp;
+                if (layer == p.layers - 1 && !(p.dbg & 128)) {
+                    int r0 = (L - K) & ~7;
+                    int n = (L - r0 + 15) & ~15;
+                    if (r0 + n > Lp) r0 = Lp - n;
+                    if (n < Lp) { rq0 = r0; nq = n; }
+                }
+                const bool pruned = nq < Lp;
                 if (Role::kCompute) {
                     // next layer's parameters: its buffer was last read before the barrier that ended the previous layer
                     if (lcount + 1 < total_layers) load_params((layer + 1) % p.layers, (lcount + 1) & 1);
@@ -468,23 +485,34 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 stamp();   // LN1
                 R.fp.mark(11);
                 // ---- packed q | k | v projection -> Y[token][3d]; q pre-scaled by log2(e)/sqrt(dh) ----
-                {
-                    const UOp op{ly.wqkv, DMODEL >> 6, 0, (3 * DMODEL) >> 7, 0, DMODEL >> 6};
-                    R.template gemm_h16<NKB * 4>(op, x_u32, kbb, Lp, s_bqkv, sm_scale_log2, DMODEL, yb);
+                // full layers: one call over q | k | v with every token.  Pruned last layer: k | v of every token, then
+                // q of the tail rows (own accumulator barriers and TMEM columns).  One call site (a 2-trip loop) so that the
+                // epilogue is instantiated once.
+#pragma unroll 1
+                for (int part = 0; part < (pruned ? 2 : 1); ++part) {
+                    const bool qpart = pruned && part == 1;
+                    const int tile0 = (pruned && part == 0) ? (DMODEL >> 7) : 0;
+                    const int ntile = !pruned ? ((3 * DMODEL) >> 7) : (qpart ? (DMODEL >> 7) : ((2 * DMODEL) >> 7));
+                    const UOp op{ly.wqkv, DMODEL >> 6, tile0, ntile, 0, DMODEL >> 6};
+                    R.template gemm_h16<NKB * 4>(op, x_u32, kbb, qpart ? nq : Lp, s_bqkv, sm_scale_log2, DMODEL, yb,
+                                                 H16Ext{tile0 * 128, qpart ? rq0 : 0, qpart ? 4 : 0,
+                                                        qpart ? (uint32_t)(((2 * DMODEL) >> 7) * Lp) : 0u});
                 }
                 R.sync();
                 stamp();   // qkv
                 R.fp.mark(12);
                 if (Role::kCompute && !(p.dbg & 32)) {
                     if (NKB <= 6) {
+                        // (the pruned last layer has nq / 16 query blocks starting at row rq0; same call, same code)
                         for (int hh = warp; hh < p.heads; hh += RO_WARPS)
                             attn_head<DH, (NKB <= 6 ? NKB : 2), (NKB <= 6 ? NKB / 2 : 1)>(
-                                yb, addr_s, nmb, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb, 1.f, lane);
+                                yb, addr_s, nq >> 4, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb, 1.f, lane, rq0);
                     } else {
-                        for (int item = warp; item < p.heads * nmb; item += RO_WARPS) {
-                            const int hh = item / nmb, mb = item % nmb;
-                            attn_block<DH, NKB>(yb, addr_s, mb, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb,
-                                                1.f, lane);
+                        const int nblk = nq >> 4;
+                        for (int item = warp; item < p.heads * nblk; item += RO_WARPS) {
+                            const int hh = item / nblk, qb = item % nblk;
+                            attn_rows<DH, NKB>(yb, addr_s, rq0 + 16 * qb, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb,
+                                               1.f, lane);
                         }
                     }
                 }
@@ -494,10 +522,10 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 // ---- h += O Wo^T + bo ----
                 {
                     const UOp op{ly.wo, DMODEL >> 6, 0, DMODEL >> 7, 0, DMODEL >> 6};
-                    R.gemm(op, y_u32, kbb, Lp,
+                    R.gemm(op, y_u32 + (uint32_t)(rq0 * 128), kbb, nq,
                            [&](int f) { return s_bo[f]; },
                            [&](int f, int t8, const float (&v)[8], float bi) {
-                               float* hf = h + t8 * (DMODEL + RU_HPAD) + f;
+                               float* hf = h + (rq0 + t8) * (DMODEL + RU_HPAD) + f;
 #pragma unroll
                                for (int i = 0; i < 8; ++i) hf[i * (DMODEL + RU_HPAD)] += v[i] + bi;
                            });
@@ -507,7 +535,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 R.fp.mark(14);
                 R.fp.mark(30);
                 if (Role::kCompute && !(p.dbg & 64))
-                    ln_to_half_q<DMODEL, RU_HPAD>(h, xb, addr_s, L, Lp, l2w, l2b, warp, lane);
+                    ln_to_half_q<DMODEL, RU_HPAD>(h, xb, addr_s, L, rq0 + nq, l2w, l2b, warp, lane, rq0);
                 R.fp.mark(31);
                 R.sync();
                 R.fp.mark(32);
@@ -517,7 +545,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 //      epilogue has written the tile; FC hidden features per chunk ----
                 for (int f0 = 0; f0 < F; f0 += FC) {
                     const int fcw = (F - f0) < FC ? (F - f0) : FC;
-                    const FfnArgs fa{ly.w1, ly.w2, s_b1, s_b2, DMODEL, F, f0, fcw, Lp, kbb, x_u32, y_u32, yb, h,
+                    const FfnArgs fa{ly.w1, ly.w2, s_b1, s_b2, DMODEL, F, f0, fcw, nq, kbb, rq0, x_u32, y_u32, yb, h,
                                      (uint32_t)((FC >> 7) * LpMax), f0 == 0, f0 + FC >= F};
                     R.template ffn<NKB * 4>(fa);
                 }
