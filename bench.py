@@ -217,15 +217,22 @@ def run_ours(args):
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # rank 0 prints ONE JSON line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION in this image's environment,
+    # printed with printf when the communicator is created) is sent to stderr instead
+    saved_stdout = None
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     if rank == 0:
         build_extension()
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     engine.load()
 
     B, T_in, T_out, K, N, C, D = (WL[k] for k in ('B', 'T_in', 'T_out', 'K', 'N', 'C', 'D'))
