@@ -103,18 +103,23 @@ struct FineProf {
 struct BProducer {
     static constexpr bool kCompute = false;
     BRing ring;
-    uint32_t pidx;
+    uint32_t pidx;            // next stage
+    uint32_t phase;           // its fill parity
     uint64_t pol;
     int dbg;
     FineProf fp;
     __device__ __forceinline__ void emit(const UOp& op) {
         for (int t = 0; t < op.ntile; ++t)
-            for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles, ++pidx) {
+            for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles) {
                 const int nk = (op.nkb - kb) < ring.stage_tiles ? (op.nkb - kb) : ring.stage_tiles;
-                const int s = pidx % ring.nstage;
+                // stage index / phase kept incrementally (pidx % nstage and pidx / nstage with a run-time nstage
+                // are ~40-cycle integer sequences on the handshake path)
+                const int s = (int)pidx;
+                const uint32_t par = phase;
+                if (++pidx == (uint32_t)ring.nstage) { pidx = 0; phase ^= 1u; }
                 // spin (no back-off): a sleeping producer adds its wake-up latency to every refill of the ring
                 fp.mark(1);
-                mbar_wait(&ring.empty[s], ((pidx / ring.nstage) & 1) ^ 1);
+                mbar_wait(&ring.empty[s], par ^ 1u);
                 fp.mark(2);
                 if (dbg & 1) { mbar_arrive(&ring.full[s]); continue; }
                 mbar_arrive_expect_tx(&ring.full[s], nk * RU_TILE_BYTES);
@@ -140,7 +145,8 @@ struct BProducer {
 struct BMma {
     static constexpr bool kCompute = false;
     BRing ring;
-    uint32_t pidx;
+    uint32_t pidx;            // next stage
+    uint32_t phase;           // its fill parity
     uint32_t tmem;
     uint64_t* bars;
     uint32_t rdypar;          // bit j = parity of the next completion of rdy[j]
@@ -153,11 +159,13 @@ struct BMma {
                                           bool acc_first, bool commit_tiles, int tbase = 0) {
         const uint32_t idesc = umma_idesc_f16(128, ntok);
         for (int t = 0; t < op.ntile; ++t) {
-            for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles, ++pidx) {
+            for (int kb = 0; kb < op.nkb; kb += ring.stage_tiles) {
                 const int nk = (op.nkb - kb) < ring.stage_tiles ? (op.nkb - kb) : ring.stage_tiles;
-                const int s = pidx % ring.nstage;
+                const int s = (int)pidx;
+                const uint32_t par = phase;
+                if (++pidx == (uint32_t)ring.nstage) { pidx = 0; phase ^= 1u; }
                 fp.mark(1);
-                mbar_wait(&ring.full[s], (pidx / ring.nstage) & 1);
+                mbar_wait(&ring.full[s], par);
                 fp.mark(2);
                 tcgen05_fence_after();
                 // descriptors are built once per stage; a K step of 16 (32 B) or the next k tile only
@@ -614,11 +622,11 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ro_umma_forward_kernel(const RO
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(RU_REGS_SERVICE));
         if (warp == RO_WARPS) {
             if (lane == 0) {
-                BProducer P{ring, 0u, l2_policy_evict_last(), p.dbg, FineProf{fine ? p.prof + 2048 : nullptr, 0, 1024, false}};
+                BProducer P{ring, 0u, 0u, l2_policy_evict_last(), p.dbg, FineProf{fine ? p.prof + 2048 : nullptr, 0, 1024, false}};
                 run_rollout_b<DMODEL, DH, NKB>(P, p, h, xb, yb, par, bars, tid, warp, lane);
             }
         } else if (warp == RO_WARPS + 1) {
-            BMma M{ring, 0u, tmem, bars, 0u, lane, p.dbg, FineProf{(fine && lane == 0) ? p.prof + 3072 : nullptr, 0, 1024, false}};
+            BMma M{ring, 0u, 0u, tmem, bars, 0u, lane, p.dbg, FineProf{(fine && lane == 0) ? p.prof + 3072 : nullptr, 0, 1024, false}};
             run_rollout_b<DMODEL, DH, NKB>(M, p, h, xb, yb, par, bars, tid, warp, lane);
         }
     } else {
