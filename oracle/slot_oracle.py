@@ -22,6 +22,8 @@ Reference lines followed (paths relative to /root/reference/slotformer):
                         batch_first=True, activation=relu), eval mode, as built
                         at slotformer.py:72-80
   * GRU cell            torch.nn.GRUCell gate order (r, z, n)
+  * decode_combine      base_slots/models/savi.py:519-523 (pinned by tests/golden/decode.npz)
+  * postproc_mask       video_prediction/vp_utils.py:20-41 (pinned by tests/golden/decode.npz)
 
 Weights are dicts keyed by the reference ``state_dict`` names, so the same
 dict loads into the reference modules (that is how the goldens are made).
