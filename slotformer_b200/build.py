@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsfb200.so')
-SOURCES = ["capi.cu", "sa_pass.cu", "sa_update.cu", "ro_kernel.cu", "ro_umma.cu", "umma_test.cu", "decode_combine.cu"]
+SOURCES = ["capi.cu", "sa_pass.cu", "sa_update.cu", "ro_kernel.cu", "ro_umma.cu", "umma_test.cu", "decode_combine.cu", "sa_pass_split.cu"]
 HEADERS = ['common.cuh', 'sa_kernel.h', 'ro_kernel.h', 'ro_attn.cuh', 'umma.cuh', 'decode_kernel.h', os.path.join('..', '..', 'include', 'sfb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '--use_fast_math', '-Xptxas', '-v']

@@ -157,7 +157,8 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
 
     // persistent streaming passes: one CTA per SM, or fewer when the caller shares the GPU with the rollout
-    { const int lim = g_sa_cta_limit.load(); if (lim > 0 && lim < di.sms) di.sms = lim; }
+    bool cta_limited = false;
+    { const int lim = g_sa_cta_limit.load(); if (lim > 0 && lim < di.sms) { di.sms = lim; cta_limited = true; } }
     const int chunk = sa_pick_chunk(B, N, C, n_iter, chunk_frames);
     sfb::SAWorkspace ws;
     sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);
@@ -190,6 +191,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     pp.B = B; pp.N = N; pp.K = K; pp.nchunk = ws.nchunk; pp.chunk_px = ws.chunk_px;
     pp.pstride = ws.pstride; pp.n16 = ws.n16; pp.xhat_frames = ws.xhat_frames > 0 ? ws.xhat_frames : 1;
     pp.prof = g_prof; pp.prof_cap = g_prof_cap;
+    pp.cta_limited = cta_limited ? 1 : 0;
     { const char* dv = getenv("SFB_DBG"); pp.dbg = dv ? atoi(dv) : 0; }
 
     for (int f0 = 0; f0 < B; f0 += chunk) {

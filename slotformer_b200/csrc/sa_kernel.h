@@ -48,6 +48,7 @@ struct SAPassParams {
     int nframes;               // frames in this launch
     unsigned long long* prof;
     int prof_cap;
+    int cta_limited;           // the grid is capped below one CTA per SM (batch pipeline): the passes are SM-bound
     int dbg;                   // debug switches (SFB_DBG env): 1 = no proxy fence, 2 = no x^ store, 4 = skip LN+MMA work
 };
 
@@ -71,6 +72,9 @@ cudaError_t sa_prep_launch(const float* wq, const float* wk, const float* wv, co
                            const float* ln_in_b, char* ws_base,
                            const SAWorkspace& ws, int C, int D, int DM, cudaStream_t st);
 cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, int smem_limit, cudaStream_t st);
+// first pass with LayerNorm and tensor-core halves of a tile on different warps (sa_pass_split.cu)
+bool sa_pass_split_supported(const SAPassParams& p, int C);
+cudaError_t sa_pass_split_launch(const SAPassParams& p, int sms, cudaStream_t st);
 cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st);
 bool sa_shape_supported(int C, int D, int DM);
 
