@@ -252,3 +252,27 @@ def test_slot_attention_slot_count_edges_vs_oracle(K, N):
         out, mask = m(torch.from_numpy(feats).to(DEV), torch.from_numpy(slots).to(DEV))
     assert rel_max(out.cpu().numpy(), ref) < 1e-3
     assert np.abs(mask.cpu().numpy() - ref_mask).max() < 2e-3
+
+
+@pytest.mark.parametrize('B,K,N,bf16', [(3, 6, 1000, False), (2, 7, 520, False), (5, 4, 4096, True), (1, 1, 64, False),
+                                        (40, 6, 4096, False)])
+def test_warp_pair_first_pass_is_bit_identical(monkeypatch, B, K, N, bf16):
+    """sa_pass1_split_kernel (LayerNorm warp + tensor-core warp per pixel-tile stream; selected under the batch
+    pipeline's CTA cap) against sa_pass_kernel on ragged / tiny / bf16 / multi-item shapes: same items, same
+    per-warp summation order, same reduction tree -> bit-identical slots."""
+    c = dict(B=B, N=N, C=128, D=128, Dm=256, K=K, iters=2, mask=False, seed=60 + K)
+    w = cases.make_sa_weights(c['C'], c['D'], c['Dm'], c['seed'])
+    feats, slots = cases.make_sa_inputs(B, N, c['C'], c['D'], K, c['seed'])
+    m = sa_module(c, w, DEV, mask=False)
+    f = torch.from_numpy(feats).to(DEV)
+    if bf16:
+        f = f.to(torch.bfloat16)
+    s0 = torch.from_numpy(slots).to(DEV)
+    with torch.no_grad():
+        monkeypatch.setenv('SFB_SA_SPLIT', '0')
+        a = m(f, s0)
+        monkeypatch.setenv('SFB_SA_SPLIT', '1')
+        b = m(f, s0)
+        b2 = m(f, s0)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b) and torch.equal(b, b2)
