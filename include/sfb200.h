@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SFB_VERSION 100 /* 0.1.0 */
+#define SFB_VERSION 200 /* 0.2.0 */
 
 #define SFB_OK 0
 #define SFB_E_BAD_SHAPE (-1)        /* unsupported / inconsistent dimensions            */
@@ -52,21 +52,22 @@ const char* sfb_strerror(int code);
 /* number of kernel launches this process has made through the library (bench.py's gpu_launches) */
 long long sfb_launch_count(void);
 
-/* Caps the grid of the persistent Slot Attention passes at `max_ctas` CTAs (0 = one per SM, the default).
- * Process-wide.  Used when Slot Attention of the next clip batch runs concurrently with the rollout of the
- * previous one (slotformer_b200.engine.HotPathPipeline): the rollout holds one SM per clip, Slot Attention is
- * HBM-bound and keeps its bandwidth on the remaining SMs. */
-int sfb_sa_set_cta_limit(int max_ctas);
+/* The library keeps no mutable state between calls (sfb_launch_count is a statistic nobody reads back): every
+ * entry point is re-entrant across host threads, streams and devices, and safe to capture into CUDA graphs. */
 
-/* Debug / profiling aids (not part of the operator surface).
+#ifdef SFB_DEBUG
+/* Debug / profiling aids: only in the debug build (python -m slotformer_b200.build --debug ->
+ * libsfb200_debug.so), never in the product library.
  * sfb_debug_set_profile: device buffer of `capacity` uint64 that the NEXT forward calls fill with
- * %globaltimer stamps at phase boundaries (cluster 0 / CTA 0); pass NULL to switch it off.
+ * %globaltimer stamps at phase boundaries (cluster 0 / CTA 0); pass NULL to switch it off.  The debug build also
+ * honours the SFB_DBG environment switches that disable parts of a kernel for timing experiments.
  */
 void sfb_debug_set_profile(void* device_buf, int capacity);
 /* self-test of the tcgen05 path: out[N][M] = X[N][K] W[M][K]^T (fp16 operands, fp32 accumulate);
  * M % 128 == 0, 16 <= N <= 128 (N % 16 == 0), K % 64 == 0; workspace >= M*K*2 bytes. */
 int sfb_debug_umma_gemm(const float* W, const float* X, float* out, int M, int N, int K, void* workspace,
                         size_t workspace_bytes, void* stream);
+#endif
 
 /* ------------------------------------------------------------------------- */
 /* Hot path 1: Slot Attention                                                 */
@@ -102,6 +103,11 @@ size_t sfb_sa_workspace_bytes(int B, int N, int C, int D, int Dm, int n_iter, in
 int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* sfb_sa_forward flags */
+#define SFB_SA_NO_TCGEN05 1u /* run the mma.sync passes (sa_pass.cu) instead of the tcgen05 ones (sa_pass_tc.cu)  */
+#define SFB_SA_SPLIT_ON 2u   /* mma.sync first pass on warp pairs: force on ...                                   */
+#define SFB_SA_SPLIT_OFF 4u  /* ... / off (default: on when max_ctas caps the grid)                                */
+
 /* Slot Attention forward for B independent frames (after sfb_sa_prepare on the same workspace).
  *   feats        [B, N, C]  fp32 (SFB_DTYPE_F32) or bf16 (SFB_DTYPE_BF16); rows contiguous, frame b at
  *                feats + b*feat_batch_stride elements (savi.py:406 passes encoder_out[:, idx])
@@ -111,13 +117,17 @@ int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspac
  *   workspace    >= sfb_sa_workspace_bytes(...) for the same arguments, 16-byte aligned
  *   chunk_frames 0 = choose; otherwise frames processed per scheduling chunk (the fp16 x^ ring
  *                of one chunk is what later iterations re-read; keep it inside L2)
+ *   max_ctas     0 = one persistent CTA per SM; otherwise the grid of the streaming passes is capped at this
+ *                many CTAs, e.g. while the rollout of the previous clip batch holds one SM per clip on another
+ *                stream (slotformer_b200.engine.HotPathPipeline).  Per call: nothing process-wide.
+ *   flags        SFB_SA_* (0 = defaults)
  * Supported: (C, D, Dm) in {(128,128,256), (192,192,384)}, 1 <= K <= 8, n_iter >= 1, N >= 1.
  */
 int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const float* slots_in, float* slots_out, float* seg_mask,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
-                   int n_iter, float eps, int chunk_frames, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   int n_iter, float eps, int chunk_frames, int max_ctas, unsigned int flags,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Hot path 2: autoregressive slot-Transformer rollout                        */
@@ -161,6 +171,9 @@ size_t sfb_rollout_workspace_bytes(int Ds, int d, int F, int num_layers);
 int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* sfb_rollout_forward flags */
+#define SFB_RO_MMA_SYNC 1u /* force engine A (mma.sync) even when the window fits the tcgen05 engine */
+
 /* Autoregressive rollout for B independent clips.
  *   hist      [B, T_h, K, Ds] fp32 burn-in slots        pred_out [B, pred_len, K, Ds] fp32
  *   mode      SFB_RO_SLIDE: window = T_h frames (pe_frames = T_h)
@@ -171,7 +184,8 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
  */
 int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights* w, int B,
                         int T_h, int K, int Ds, int d, int F, int heads, int pred_len, int mode,
-                        int cond_len, const void* workspace, size_t workspace_bytes, void* stream);
+                        int cond_len, unsigned int flags, const void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Decoder epilogue (next row f2): the tail of StoSAVi.decode + postproc_mask   */

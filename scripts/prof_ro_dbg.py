@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 import torch, bench
 from slotformer_b200.video_prediction.models import SlotRollouter
+from slotformer_b200 import engine
+engine.use_debug_library()   # the SFB_DBG switches exist only in the -DSFB_DEBUG build
 dev = 'cuda:0'; WL = bench.WL
 _, ro_w = bench.make_weights()
 ro = SlotRollouter(WL['K'], WL['D'], WL['T_in'], d_model=WL['d'], num_layers=WL['layers'], num_heads=WL['heads'], ffn_dim=WL['F'])

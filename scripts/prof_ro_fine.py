@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden
 import numpy as np, torch, bench
 from slotformer_b200 import engine
 from slotformer_b200.video_prediction.models import SlotRollouter
-dev = 'cuda:0'; WL = bench.WL; lib = engine.load()
+dev = 'cuda:0'; WL = bench.WL; lib = engine.use_debug_library()   # -DSFB_DEBUG build: timeline hook + SFB_DBG switches
 _, ro_w = bench.make_weights()
 ro = SlotRollouter(WL['K'], WL['D'], WL['T_in'], d_model=WL['d'], num_layers=WL['layers'], num_heads=WL['heads'], ffn_dim=WL['F'])
 ro.load_state_dict({k: torch.from_numpy(v) for k, v in ro_w.items()}, strict=False); ro = ro.to(dev).eval()

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden
 import numpy as np, torch, bench
 from slotformer_b200 import engine
 from slotformer_b200.video_prediction.models import SlotRollouter
-dev = 'cuda:0'; WL = dict(bench.WL); lib = engine.load()
+dev = 'cuda:0'; WL = dict(bench.WL); lib = engine.use_debug_library()   # -DSFB_DEBUG build: timeline hook + SFB_DBG switches
 CASE = os.environ.get('RO_CASE')          # e.g. RO_CASE=ro_cfg3: a tests/golden/cases.py rollout case instead of the bench workload
 if CASE:
     sys.path.insert(0, os.path.join(ROOT, 'tests'))

@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 import torch, bench
 from slotformer_b200 import engine
+engine.use_debug_library()   # the SFB_DBG switches exist only in the -DSFB_DEBUG build
 from slotformer_b200.base_slots.models import SlotAttention
 WL = bench.WL; dev = 'cuda:0'
 sa_w, _ = bench.make_weights()
@@ -13,7 +14,7 @@ sa = SlotAttention(WL['C'], WL['iters'], WL['K'], WL['D'], WL['Dm']); sa.load_st
 feats = torch.randn((384, 4096, 128), device=dev); init = torch.randn((384, 6, 128), device=dev)
 with torch.no_grad():
     for lim in (0, 84):
-        engine.set_sa_cta_limit(lim)
+        sa.max_ctas = lim
         for dbg in (0,):
             os.environ['SFB_DBG'] = str(dbg)
             for _ in range(3): sa(feats, init)

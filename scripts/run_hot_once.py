@@ -14,7 +14,9 @@ sa = SlotAttention(WL['C'], WL['iters'], WL['K'], WL['D'], WL['Dm']); sa.load_st
 ro = SlotRollouter(WL['K'], WL['D'], WL['T_in'], d_model=WL['d'], num_layers=WL['layers'], num_heads=WL['heads'], ffn_dim=WL['F'])
 ro.load_state_dict({k: torch.from_numpy(v) for k, v in ro_w.items()}, strict=False); ro = ro.to(dev).eval()
 feats = torch.randn((384, 4096, 128), device=dev); init = torch.randn((384, 6, 128), device=dev)
-engine.set_sa_cta_limit(int(os.environ.get('SA_CTAS', '0')))
+sa.max_ctas = int(os.environ.get('SA_CTAS', '0'))
+if os.environ.get('SA_NO_TC'):
+    sa.engine_flags = engine.SFB_SA_NO_TCGEN05
 with torch.no_grad():
     for _ in range(int(os.environ.get('REPS', '3'))):
         s = sa(feats, init)

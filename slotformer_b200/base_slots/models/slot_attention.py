@@ -37,6 +37,8 @@ class SlotAttention(nn.Module):
                                  nn.Linear(mlp_hidden_size, slot_size))
         self._engine = SlotAttentionEngine()
         self.chunk_frames = 0   # 0 = let the engine size the frame chunks (fp16 x^ ring inside L2)
+        self.max_ctas = 0       # 0 = one persistent CTA per SM; HotPathPipeline caps it while a rollout runs alongside
+        self.engine_flags = 0   # engine.SFB_SA_* (tests select the mma.sync passes with it)
 
     # -- helpers ---------------------------------------------------------- #
     def _weights(self):
@@ -79,7 +81,7 @@ class SlotAttention(nn.Module):
             slots.detach().float(),
             {k: v.detach() for k, v in self._weights().items()},
             self.num_iterations, self.eps, self.mlp_hidden_size, return_mask=return_mask,
-            chunk_frames=self.chunk_frames)
+            chunk_frames=self.chunk_frames, max_ctas=self.max_ctas, flags=self.engine_flags)
 
     def forward(self, inputs, slots):
         """inputs [B, N, C] flattened per-pixel features; slots [B, K, D] initial slots.

@@ -11,10 +11,18 @@
 
 namespace {
 
-std::atomic<long long> g_launches{0};
-std::atomic<int> g_sa_cta_limit{0};     // 0 = every SM; see sfb_sa_set_cta_limit
-unsigned long long* g_prof = nullptr;   // debug timeline buffer (device), see sfb_debug_set_profile
+std::atomic<long long> g_launches{0};    // statistics only (sfb_launch_count); no call reads it
+#ifdef SFB_DEBUG
+// Debug build only (python -m slotformer_b200.build --debug -> libsfb200_debug.so): timeline buffer and the
+// SFB_DBG kernel switches.  The product library has neither: its calls depend on their arguments alone.
+unsigned long long* g_prof = nullptr;   // device buffer, see sfb_debug_set_profile
 int g_prof_cap = 0;
+int debug_switches() { const char* dv = getenv("SFB_DBG"); return dv ? atoi(dv) : 0; }
+#else
+constexpr unsigned long long* g_prof = nullptr;
+constexpr int g_prof_cap = 0;
+constexpr int debug_switches() { return 0; }
+#endif
 
 inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? SFB_OK : (SFB_E_CUDA_BASE - (int)e); }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -52,20 +60,14 @@ extern "C" {
 
 int sfb_version(void) { return SFB_VERSION; }
 
+#ifdef SFB_DEBUG
 void sfb_debug_set_profile(void* device_buf, int capacity) {
     g_prof = reinterpret_cast<unsigned long long*>(device_buf);
     g_prof_cap = device_buf ? capacity : 0;
 }
-
-
+#endif
 
 long long sfb_launch_count(void) { return g_launches.load(); }
-
-int sfb_sa_set_cta_limit(int max_ctas) {
-    if (max_ctas < 0) return SFB_E_BAD_SHAPE;
-    g_sa_cta_limit.store(max_ctas);
-    return SFB_OK;
-}
 
 const char* sfb_strerror(int code) {
     switch (code) {
@@ -81,6 +83,7 @@ const char* sfb_strerror(int code) {
     return "unknown error";
 }
 
+#ifdef SFB_DEBUG
 int sfb_debug_umma_gemm(const float* W, const float* X, float* out, int M, int N, int K, void* workspace,
                         size_t workspace_bytes, void* stream) {
     if (!W || !X || !out || !workspace) return SFB_E_NULL;
@@ -92,6 +95,7 @@ int sfb_debug_umma_gemm(const float* W, const float* X, float* out, int M, int N
     e = sfb::umma_test_launch(reinterpret_cast<const __half*>(workspace), X, out, M, N, K, st);
     return cuda_err(e);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Slot Attention
@@ -137,14 +141,14 @@ int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspac
 int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const float* slots_in, float* slots_out, float* seg_mask,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
-                   int n_iter, float eps, int chunk_frames, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   int n_iter, float eps, int chunk_frames, int max_ctas, unsigned int flags,
+                   void* workspace, size_t workspace_bytes, void* stream) {
     if (B == 0) return SFB_OK;
     if (!feats || !slots_in || !slots_out || !w || !workspace) return SFB_E_NULL;
     const float* const* wp = reinterpret_cast<const float* const*>(w);
     for (size_t i = 0; i < sizeof(sfb_sa_weights) / sizeof(const float*); ++i)
         if (!wp[i]) return SFB_E_NULL;
-    if (B < 0 || N < 1 || K < 1 || K > 8 || n_iter < 1) return SFB_E_BAD_SHAPE;
+    if (B < 0 || N < 1 || K < 1 || K > 8 || n_iter < 1 || max_ctas < 0) return SFB_E_BAD_SHAPE;
     if (feat_dtype != SFB_DTYPE_F32 && feat_dtype != SFB_DTYPE_BF16) return SFB_E_BAD_SHAPE;
     if (!sfb::sa_shape_supported(C, D, Dm)) return SFB_E_BAD_SHAPE;
     if (feat_batch_stride < (int64_t)N * C || (feat_batch_stride & 7)) return SFB_E_BAD_ALIGN;
@@ -158,7 +162,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
 
     // persistent streaming passes: one CTA per SM, or fewer when the caller shares the GPU with the rollout
     bool cta_limited = false;
-    { const int lim = g_sa_cta_limit.load(); if (lim > 0 && lim < di.sms) { di.sms = lim; cta_limited = true; } }
+    if (max_ctas > 0 && max_ctas < di.sms) { di.sms = max_ctas; cta_limited = true; }
     const int chunk = sa_pick_chunk(B, N, C, n_iter, chunk_frames);
     sfb::SAWorkspace ws;
     sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);
@@ -192,7 +196,11 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     pp.pstride = ws.pstride; pp.n16 = ws.n16; pp.xhat_frames = ws.xhat_frames > 0 ? ws.xhat_frames : 1;
     pp.prof = g_prof; pp.prof_cap = g_prof_cap;
     pp.cta_limited = cta_limited ? 1 : 0;
-    { const char* dv = getenv("SFB_DBG"); pp.dbg = dv ? atoi(dv) : 0; }
+    pp.split = (flags & SFB_SA_SPLIT_ON) ? 1 : ((flags & SFB_SA_SPLIT_OFF) ? 0 : -1);
+    pp.dbg = debug_switches();
+    // tcgen05 passes (C = 128) unless the caller asks for the mma.sync ones; q~ then lives in the operand layout
+    const bool use_tc = !(flags & SFB_SA_NO_TCGEN05) && sfb::sa_pass_tc_supported(pp, C);
+    up.qt_swz = use_tc ? 1 : 0;
 
     for (int f0 = 0; f0 < B; f0 += chunk) {
         const int nf = (B - f0) < chunk ? (B - f0) : chunk;
@@ -206,7 +214,9 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
             const bool last = (it == n_iter - 1);
             pp.xhat = (n_iter > 1) ? reinterpret_cast<__half*>(base + ws.xhat) : nullptr;
             pp.seg_mask = last ? seg_mask : nullptr;
-            if ((e = sfb::sa_pass_launch(pp, C, it == 0, di.sms, di.smem_optin, st)) != cudaSuccess) return cuda_err(e);
+            e = use_tc ? sfb::sa_pass_tc_launch(pp, it == 0, di.sms, st)
+                       : sfb::sa_pass_launch(pp, C, it == 0, di.sms, di.smem_optin, st);
+            if (e != cudaSuccess) return cuda_err(e);
             g_launches.fetch_add(1);
             up.do_update = 1; up.do_q = last ? 0 : 1; up.first = (it == 0);
             up.slots_prev = (it == 0) ? slots_in : slots_out;
@@ -289,7 +299,8 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
 
 int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights* w, int B,
                         int T_h, int K, int Ds, int d, int F, int heads, int pred_len, int mode,
-                        int cond_len, const void* workspace, size_t workspace_bytes, void* stream) {
+                        int cond_len, unsigned int flags, const void* workspace, size_t workspace_bytes,
+                        void* stream) {
     if (B == 0 || pred_len == 0) return SFB_OK;
     if (!hist || !pred_out || !w || !workspace) return SFB_E_NULL;
     if (B < 0 || T_h < 1 || K < 1 || K > 16 || pred_len < 0) return SFB_E_BAD_SHAPE;
@@ -330,11 +341,10 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     p.pe_tokens = p.cond_tokens;
     p.lmax = p.cond_tokens;
     p.prof = g_prof; p.prof_cap = g_prof_cap;
-    { const char* dv = getenv("SFB_DBG"); p.dbg = dv ? atoi(dv) : 0; }
+    p.dbg = debug_switches();
     size_t smem = 0;
-    // engine B (tcgen05 + TMEM) when the window fits on chip, else engine A (mma.sync); SFB_RO_ENGINE=mma forces A
-    const char* eng = getenv("SFB_RO_ENGINE");
-    const bool force_mma = eng && eng[0] == 'm';
+    // engine B (tcgen05 + TMEM) when the window fits on chip, else engine A (mma.sync); SFB_RO_MMA_SYNC forces A
+    const bool force_mma = (flags & SFB_RO_MMA_SYNC) != 0;
     cudaError_t e;
     if (!force_mma && sfb::ro_umma_plan(&p, di.smem_optin, &smem) == 0) {
         e = sfb::ro_umma_launch(p, smem, reinterpret_cast<cudaStream_t>(stream));

@@ -49,7 +49,8 @@ struct SAPassParams {
     unsigned long long* prof;
     int prof_cap;
     int cta_limited;           // the grid is capped below one CTA per SM (batch pipeline): the passes are SM-bound
-    int dbg;                   // debug switches (SFB_DBG env): 1 = no proxy fence, 2 = no x^ store, 4 = skip LN+MMA work
+    int split;                 // mma.sync first pass on warp pairs: 1 / 0 = forced on / off, -1 = when the grid is capped
+    int dbg;                   // debug switches (debug build, SFB_DBG env): 1 = no proxy fence, 2 = no x^ store, 4 = skip LN+MMA work
 };
 
 struct SAUpdateParams {
@@ -63,6 +64,7 @@ struct SAUpdateParams {
     int B, N, K, nchunk, pstride;
     int frame0, nframes;
     int do_update, do_q, first;
+    int qt_swz;                // q~ written as the swizzled tcgen05 operand image (sa_pass_tc.cu) instead of [hi | lo] rows
     float eps;
 };
 
@@ -75,6 +77,9 @@ cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, in
 // first pass with LayerNorm and tensor-core halves of a tile on different warps (sa_pass_split.cu)
 bool sa_pass_split_supported(const SAPassParams& p, int C);
 cudaError_t sa_pass_split_launch(const SAPassParams& p, int sms, cudaStream_t st);
+// tcgen05 passes (sa_pass_tc.cu): C = 128; q~ must be in the swizzled operand layout (SAUpdateParams::qt_swz)
+bool sa_pass_tc_supported(const SAPassParams& p, int C);
+cudaError_t sa_pass_tc_launch(const SAPassParams& p, bool first, int sms, cudaStream_t st);
 cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st);
 bool sa_shape_supported(int C, int D, int DM);
 

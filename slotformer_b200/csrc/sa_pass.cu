@@ -23,7 +23,6 @@
 //     over all frames, tensor cores with 3-term fp16 splitting (hi*hi + lo*hi + hi*lo ~ fp32).
 #include "common.cuh"
 #include "sa_kernel.h"
-#include <cstdlib>
 
 namespace sfb {
 
@@ -488,9 +487,8 @@ cudaError_t sa_pass_launch(const SAPassParams& p, int C, bool first, int sms, in
     (void)smem_limit;
     {
         // warp-pair first pass (sa_pass_split.cu): 9 % faster when the grid is capped (SM-bound, 633 -> 576 us per
-        // Slot Attention call at 84 CTAs), 1 % slower with every SM (HBM-bound); SFB_SA_SPLIT=0/1 overrides
-        const char* e = getenv("SFB_SA_SPLIT");
-        const bool want = e ? (atoi(e) != 0) : (p.cta_limited != 0);
+        // Slot Attention call at 84 CTAs), 1 % slower with every SM (HBM-bound); SFB_SA_SPLIT_ON / _OFF override
+        const bool want = p.split >= 0 ? (p.split != 0) : (p.cta_limited != 0);
         if (first && want && sa_pass_split_supported(p, C)) return sa_pass_split_launch(p, sms, st);
     }
     const bool bf16 = p.feat_esize == 2;

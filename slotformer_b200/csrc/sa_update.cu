@@ -456,10 +456,20 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
                         const int row = 16 * mb + g + 8 * (e >> 1), col = col0 + (e & 1);
                         if (fl0 + (row >> 3) < p.nframes) {
                             const float v = ((row & 7) < K) ? acc[mb][e] : 0.f;
-                            __half* qh = p.qt + (size_t)(fbase + (row >> 3)) * p.qt_stride + (row & 7) * C + col;
+                            __half* qf = p.qt + (size_t)(fbase + (row >> 3)) * p.qt_stride;
                             const __half hv = __float2half_rn(v);
-                            qh[0] = hv;
-                            qh[8 * C] = __float2half_rn(v - __half2float(hv));
+                            const __half lv = __float2half_rn(v - __half2float(hv));
+                            if (p.qt_swz) {
+                                // tcgen05 B operand image (sa_pass_tc.cu): rows 0-7 = hi, 8-15 = lo, two 64-channel
+                                // K-major panels of 16 rows x 128 B, 16-byte chunks XOR-swizzled by the row
+                                const int r = row & 7;
+                                const int off = (col >> 6) * 1024 + ((((col & 63) >> 3) ^ r) << 3) + (col & 7);
+                                qf[off + r * 64] = hv;
+                                qf[off + (8 + r) * 64] = lv;
+                            } else {
+                                qf[(row & 7) * C + col] = hv;
+                                qf[8 * C + (row & 7) * C + col] = lv;
+                            }
                         }
                     }
             }

@@ -11,7 +11,15 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, 'lib', 'libsfb200.so')
+_LIB_DEBUG_PATH = os.path.join(_HERE, 'lib', 'libsfb200_debug.so')
 _lib = None
+_lib_debug = None
+
+# sfb_sa_forward / sfb_rollout_forward flags (include/sfb200.h)
+SFB_SA_NO_TCGEN05 = 1
+SFB_SA_SPLIT_ON = 2
+SFB_SA_SPLIT_OFF = 4
+SFB_RO_MMA_SYNC = 1
 
 SFB_DTYPE_F32 = 0
 SFB_DTYPE_BF16 = 1
@@ -54,27 +62,19 @@ def lib_path():
     return _LIB_PATH
 
 
-def load():
-    """Load libsfb200.so (once).  Raises SfbError if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(_LIB_PATH):
-        raise SfbError(f'{_LIB_PATH} is missing: run `python -m slotformer_b200.build` '
-                       '(there is no fallback path)')
-    lib = ctypes.CDLL(_LIB_PATH)
+def _bind(path, debug):
+    lib = ctypes.CDLL(path)
     c = ctypes
     lib.sfb_version.restype = c.c_int
     lib.sfb_strerror.restype = c.c_char_p
     lib.sfb_strerror.argtypes = [c.c_int]
     lib.sfb_launch_count.restype = c.c_longlong
-    lib.sfb_sa_set_cta_limit.restype = c.c_int
-    lib.sfb_sa_set_cta_limit.argtypes = [c.c_int]
-    lib.sfb_debug_set_profile.restype = None
-    lib.sfb_debug_set_profile.argtypes = [c.c_void_p, c.c_int]
-    lib.sfb_debug_umma_gemm.restype = c.c_int
-    lib.sfb_debug_umma_gemm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int,
-                                        c.c_void_p, c.c_size_t, c.c_void_p]
+    if debug:
+        lib.sfb_debug_set_profile.restype = None
+        lib.sfb_debug_set_profile.argtypes = [c.c_void_p, c.c_int]
+        lib.sfb_debug_umma_gemm.restype = c.c_int
+        lib.sfb_debug_umma_gemm.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int,
+                                            c.c_void_p, c.c_size_t, c.c_void_p]
     lib.sfb_sa_workspace_bytes.restype = c.c_size_t
     lib.sfb_sa_workspace_bytes.argtypes = [c.c_int] * 7
     lib.sfb_sa_prepare.restype = c.c_int
@@ -84,7 +84,7 @@ def load():
     lib.sfb_sa_forward.argtypes = [
         c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p,
         c.POINTER(_SAWeights), c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
-        c.c_float, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
+        c.c_float, c.c_int, c.c_int, c.c_uint, c.c_void_p, c.c_size_t, c.c_void_p]
     lib.sfb_rollout_workspace_bytes.restype = c.c_size_t
     lib.sfb_rollout_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int]
     lib.sfb_rollout_prepare.restype = c.c_int
@@ -93,7 +93,7 @@ def load():
     lib.sfb_rollout_forward.restype = c.c_int
     lib.sfb_rollout_forward.argtypes = [
         c.c_void_p, c.c_void_p, c.POINTER(_ROWeights), c.c_int, c.c_int, c.c_int, c.c_int,
-        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_uint, c.c_void_p, c.c_size_t,
         c.c_void_p]
     lib.sfb_decode_combine.restype = c.c_int
     lib.sfb_decode_combine.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
@@ -101,21 +101,51 @@ def load():
     lib.sfb_postproc_mask.restype = c.c_int
     lib.sfb_postproc_mask.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_float,
                                       c.c_void_p]
-    _lib = lib
     return lib
 
 
-def exported_symbols():
+def load():
+    """Load libsfb200.so (once).  Raises SfbError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise SfbError(f'{_LIB_PATH} is missing: run `python -m slotformer_b200.build` '
+                           '(there is no fallback path)')
+        _lib = _bind(_LIB_PATH, debug=False)
+    return _lib
+
+
+def load_debug():
+    """Load libsfb200_debug.so (-DSFB_DEBUG: tcgen05 self-test, timeline hook, SFB_DBG kernel switches); used by
+    tests/test_gpu_umma.py and scripts/prof_*.py only."""
+    global _lib_debug
+    if _lib_debug is None:
+        if not os.path.exists(_LIB_DEBUG_PATH):
+            raise SfbError(f'{_LIB_DEBUG_PATH} is missing: run `python -m slotformer_b200.build --debug`')
+        _lib_debug = _bind(_LIB_DEBUG_PATH, debug=True)
+    return _lib_debug
+
+
+def use_debug_library():
+    """Route every engine call of this process through the debug build (profiling scripts)."""
+    global _lib
+    _lib = load_debug()
+    return _lib
+
+
+def exported_symbols(debug=False):
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
-    return ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_set_cta_limit', 'sfb_debug_set_profile',
-            'sfb_debug_umma_gemm', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
-            'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
-            'sfb_rollout_forward', 'sfb_decode_combine', 'sfb_postproc_mask']
+    names = ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
+             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
+             'sfb_rollout_forward', 'sfb_decode_combine', 'sfb_postproc_mask']
+    if debug:
+        names += ['sfb_debug_set_profile', 'sfb_debug_umma_gemm']
+    return names
 
 
 def umma_gemm(W, X):
-    """Self-test hook: X [N,K] @ W[M,K]^T on the tcgen05 path (fp16 operands, fp32 accumulate)."""
-    lib = load()
+    """Self-test hook (debug build): X [N,K] @ W[M,K]^T on the tcgen05 path (fp16 operands, fp32 accumulate)."""
+    lib = load_debug()
     _require_cuda_f32('W', W)
     _require_cuda_f32('X', X)
     M, K = W.shape
@@ -130,11 +160,6 @@ def umma_gemm(W, X):
 
 def launch_count():
     return int(load().sfb_launch_count())
-
-
-def set_sa_cta_limit(max_ctas):
-    """Cap the grid of the persistent Slot Attention passes (0 = one CTA per SM)."""
-    _check(load().sfb_sa_set_cta_limit(int(max_ctas)))
 
 
 class HotPathPipeline:
@@ -155,7 +180,9 @@ class HotPathPipeline:
         self.sa_ctas = sms - clips if 0 < clips <= sms // 2 else 0     # 0: no partition, plain stream order
 
     def __enter__(self):
-        set_sa_cta_limit(self.sa_ctas)
+        # the CTA cap is an argument of every sfb_sa_forward call made through this module while the pipeline is open
+        self._saved_ctas = self.sa.max_ctas
+        self.sa.max_ctas = self.sa_ctas
         cur = torch.cuda.current_stream(self.device)
         self.s_sa.wait_stream(cur)
         self.s_ro.wait_stream(cur)
@@ -165,7 +192,7 @@ class HotPathPipeline:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.s_sa)
         cur.wait_stream(self.s_ro)
-        set_sa_cta_limit(0)
+        self.sa.max_ctas = self._saved_ctas
         return False
 
     def capture(self, batches, clips, frames_per_clip, pred_len):
@@ -251,9 +278,15 @@ class SlotAttentionEngine:
     def __init__(self):
         self._ws = None
         self._key = None
+        self._captured = []      # workspaces referenced by live CUDA graphs: never freed under them
+
+    def invalidate(self):
+        """Forget the folded weights (call after in-place weight updates that bypass autograd's version counter,
+        e.g. ``p.data.copy_``): the next call runs sfb_sa_prepare again."""
+        self._key = None
 
     def forward(self, feats, slots, weights, num_iterations, eps, mlp_hidden_size,
-                return_mask=False, chunk_frames=0):
+                return_mask=False, chunk_frames=0, max_ctas=0, flags=0):
         """feats [B,N,C] f32 (rows contiguous; batch stride free), slots [B,K,D] f32.
 
         ``weights``: dict state_dict-key -> CUDA f32 tensor (SA_WEIGHT_KEYS).
@@ -285,6 +318,8 @@ class SlotAttentionEngine:
         if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             self._key = None
+        if torch.cuda.is_current_stream_capturing() and not any(w is self._ws for w in self._captured):
+            self._captured.append(self._ws)      # a graph now holds this pointer: keep it alive after a realloc
         wt = []
         cw = _SAWeights()
         for k in SA_WEIGHT_KEYS:
@@ -305,7 +340,7 @@ class SlotAttentionEngine:
                 feats.data_ptr(), feat_dtype, bstride, slots.data_ptr(), out.data_ptr(),
                 mask.data_ptr() if return_mask else None, ctypes.byref(cw), B, N, C, D,
                 int(mlp_hidden_size), K, int(num_iterations), float(eps), int(chunk_frames),
-                self._ws.data_ptr(), ws_bytes, _stream(dev))
+                int(max_ctas), int(flags), self._ws.data_ptr(), ws_bytes, _stream(dev))
         _check(rc)
         if return_mask:
             return out, mask
@@ -321,9 +356,13 @@ class RolloutEngine:
     def __init__(self):
         self._ws = None
         self._key = None
+        self._captured = []
+
+    def invalidate(self):
+        self._key = None
 
     def forward(self, hist, weights, enc_pe, num_layers, num_heads, pred_len, mode='slide',
-                cond_len=0):
+                cond_len=0, flags=0):
         """hist [B,T_h,K,Ds] f32 -> [B,pred_len,K,Ds] f32.
 
         ``weights``: dict of SlotRollouter state_dict keys -> CUDA f32 tensors.
@@ -370,6 +409,8 @@ class RolloutEngine:
             if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
                 self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 self._key = None
+            if torch.cuda.is_current_stream_capturing() and not any(w is self._ws for w in self._captured):
+                self._captured.append(self._ws)
             key = _weights_key(keep)
             if key != self._key:
                 _check(lib.sfb_rollout_prepare(ctypes.byref(cw), Ds, d, F, self._ws.data_ptr(),
@@ -378,7 +419,7 @@ class RolloutEngine:
             rc = lib.sfb_rollout_forward(
                 hist.data_ptr(), out.data_ptr(), ctypes.byref(cw), B, T_h, K, Ds, d, F,
                 int(num_heads), int(pred_len), SFB_RO_GROW if mode == 'grow' else SFB_RO_SLIDE,
-                int(cond_len or 0), self._ws.data_ptr(), ws_bytes, _stream(dev))
+                int(cond_len or 0), int(flags), self._ws.data_ptr(), ws_bytes, _stream(dev))
         _check(rc)
         return out
 

@@ -132,7 +132,7 @@ class SlotRollouter(Rollouter):
         return self._engine.forward(
             x.detach().float(), self._weights(), self._token_pe().detach().float(),
             self.num_layers, self.num_heads, pred_len, mode=self._mode,
-            cond_len=getattr(self, 'cond_len', 0))
+            cond_len=getattr(self, 'cond_len', 0), flags=getattr(self, 'engine_flags', 0))
 
     @property
     def dtype(self):

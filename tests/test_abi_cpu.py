@@ -17,19 +17,39 @@ def lib():
     return engine.load()
 
 
-def test_exports_every_declared_symbol(lib):
-    from slotformer_b200 import engine
+def _declared(debug):
     with open(os.path.join(ROOT, 'include', 'sfb200.h')) as f:
         text = f.read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    declared = set(re.findall(r'\b(sfb_[a-z_]+)\s*\(', text))
+    if not debug:
+        text = re.sub(r'#ifdef SFB_DEBUG.*?#endif', '', text, flags=re.S)
+    return set(re.findall(r'\b(sfb_[a-z0-9_]+)\s*\(', text))
+
+
+def test_exports_every_declared_symbol(lib):
+    from slotformer_b200 import engine
+    declared = _declared(debug=False)
     assert declared == set(engine.exported_symbols())
     for name in declared:
         assert getattr(lib, name) is not None
+    # the product library carries no debug hooks and no process-wide knobs
+    for name in ('sfb_debug_set_profile', 'sfb_debug_umma_gemm', 'sfb_sa_set_cta_limit'):
+        assert not hasattr(lib, name)
+
+
+def test_debug_library_exports_the_debug_hooks():
+    from slotformer_b200.build import build_extension
+    from slotformer_b200 import engine
+    build_extension(debug=True)
+    dbg = engine.load_debug()
+    declared = _declared(debug=True)
+    assert declared == set(engine.exported_symbols(debug=True))
+    for name in declared:
+        assert getattr(dbg, name) is not None
 
 
 def test_version_and_strerror(lib):
-    assert lib.sfb_version() == 100
+    assert lib.sfb_version() == 200
     assert lib.sfb_strerror(0) == b'ok'
     assert b'shape' in lib.sfb_strerror(-1)
     assert b'aligned' in lib.sfb_strerror(-2)
@@ -60,10 +80,10 @@ def test_null_and_shape_validation_without_gpu(lib):
     from slotformer_b200.engine import _SAWeights, _ROWeights
     w = _SAWeights()
     assert lib.sfb_sa_forward(None, 0, 0, None, None, None, ctypes.byref(w), 1, 64, 128, 128,
-                              256, 4, 1, 1e-6, 0, None, 0, None) == -5
+                              256, 4, 1, 1e-6, 0, 0, 0, None, 0, None) == -5
     rw = _ROWeights()
     assert lib.sfb_rollout_forward(None, None, ctypes.byref(rw), 1, 1, 1, 128, 128, 512, 8, 1,
-                                   0, 0, None, 0, None) == -5
+                                   0, 0, 0, None, 0, None) == -5
     assert lib.sfb_rollout_prepare(None, 128, 128, 512, None, 0, None) == -5
 
 

@@ -15,6 +15,7 @@ import torch
 import cases
 from helpers import golden, rel_max, ro_module, sa_module
 from oracle import slot_oracle as O
+from slotformer_b200 import engine
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -194,7 +195,6 @@ def test_empty_batch():
 def test_hot_path_pipeline_matches_serial_calls():
     """Two-stream pipeline (Slot Attention of batch i+1 concurrent with the rollout of batch i, SM-limited
     passes): bit-identical to calling the two modules back to back, for several batches in flight."""
-    from slotformer_b200 import engine
     c, w, _, _ = cases.sa_case('sa_cfg2')
     sa = sa_module(c, w, DEV, mask=False)
     rc, rw, _ = cases.ro_case('ro_cfg2')
@@ -220,7 +220,7 @@ def test_hot_path_pipeline_matches_serial_calls():
         assert torch.equal(s, rs) and torch.equal(p, rp)
 
 
-def test_rollout_mma_engine_matches_tcgen05_engine_and_repeats(monkeypatch):
+def test_rollout_mma_engine_matches_tcgen05_engine_and_repeats():
     """Engine A (mma.sync, used when a window does not fit engine B) on a d = 256 BASELINE shape at full batch:
     repeat runs are bit identical (a stage-release race once made them differ in a few clips per launch) and the
     result agrees with engine B within the rollout tolerance."""
@@ -231,7 +231,7 @@ def test_rollout_mma_engine_matches_tcgen05_engine_and_repeats(monkeypatch):
     x = torch.randn((256,) + hist.shape[1:], device=DEV, generator=gen)
     with torch.no_grad():
         b = m(x, c['pred_len'])
-        monkeypatch.setenv('SFB_RO_ENGINE', 'mma')
+        m.engine_flags = engine.SFB_RO_MMA_SYNC
         a = m(x, c['pred_len'])
         for _ in range(3):
             assert torch.equal(a, m(x, c['pred_len']))
@@ -256,7 +256,7 @@ def test_slot_attention_slot_count_edges_vs_oracle(K, N):
 
 @pytest.mark.parametrize('B,K,N,bf16', [(3, 6, 1000, False), (2, 7, 520, False), (5, 4, 4096, True), (1, 1, 64, False),
                                         (40, 6, 4096, False)])
-def test_warp_pair_first_pass_is_bit_identical(monkeypatch, B, K, N, bf16):
+def test_warp_pair_first_pass_is_bit_identical(B, K, N, bf16):
     """sa_pass1_split_kernel (LayerNorm warp + tensor-core warp per pixel-tile stream; selected under the batch
     pipeline's CTA cap) against sa_pass_kernel on ragged / tiny / bf16 / multi-item shapes: same items, same
     per-warp summation order, same reduction tree -> bit-identical slots."""
@@ -269,9 +269,9 @@ def test_warp_pair_first_pass_is_bit_identical(monkeypatch, B, K, N, bf16):
         f = f.to(torch.bfloat16)
     s0 = torch.from_numpy(slots).to(DEV)
     with torch.no_grad():
-        monkeypatch.setenv('SFB_SA_SPLIT', '0')
+        m.engine_flags = engine.SFB_SA_NO_TCGEN05 | engine.SFB_SA_SPLIT_OFF
         a = m(f, s0)
-        monkeypatch.setenv('SFB_SA_SPLIT', '1')
+        m.engine_flags = engine.SFB_SA_NO_TCGEN05 | engine.SFB_SA_SPLIT_ON
         b = m(f, s0)
         b2 = m(f, s0)
     assert torch.isfinite(a).all()
