@@ -16,8 +16,10 @@ frames/s = B * (T_in + T_out) / time.  Synthetic inputs, seeded weights (tests/g
             region.
   roofline: the Slot Attention kernel against the measured HBM peak (algorithmic bytes =
             N*C*4 + 2*K*D*4 per frame).
-  cpu_baseline / --impl reference: the numpy oracle (oracle/slot_oracle.py, fp32, all host
-            cores through BLAS) on a bounded sample of the same workload.
+  cpu_baseline / --impl reference: the UNMODIFIED reference modules (oracle/_ref, collected by
+            oracle/build_ref.py) on the host cores, full 64-clip steps (kind "reference").
+  gpu_eager_baseline: the same unmodified modules in PyTorch eager on the same GPU (fp32 and
+            bf16 autocast) -- the ">= 10x reference single-GPU forward" denominator.
 """
 import argparse
 import json
@@ -123,78 +125,129 @@ class ClockSampler(threading.Thread):
         return out
 
 
-# ---- CPU baseline (numpy oracle) --------------------------------------------------------
+# ---- reference arms: the UNMODIFIED reference modules (oracle/_ref, see oracle/build_ref.py) ------------
 def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = [i.get('num_threads', 1) for i in threadpool_info() if i.get('user_api') == 'blas']
-        if n:
-            return int(max(n))
-    except Exception:  # noqa: BLE001
-        pass
     return os.cpu_count() or 1
 
 
-def _all_cores():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is allowed every host core."""
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=os.cpu_count() or 1)
-    except Exception:  # noqa: BLE001
-        pass
-
-
-def cpu_sample_step(sa_w, ro_w, pe, clips):
-    """One bounded sample of the workload on the host: `clips` clips (clips*T_in frames)."""
-    _all_cores()
-    from oracle import slot_oracle as O
-    import cases
-    feats, slots = cases.make_sa_inputs(clips * WL['T_in'], WL['N'], WL['C'], WL['D'], WL['K'], seed=1)
-    t0 = time.perf_counter()
-    s = O.slot_attention(feats, slots, sa_w, WL['iters'], dtype=np.float32)
-    w = dict(ro_w)
-    w['enc_t_pe'] = pe
-    hist = s.reshape(clips, WL['T_in'], WL['K'], WL['D'])
-    O.rollout(hist, w, WL['T_out'], WL['heads'], WL['layers'], dtype=np.float32)
-    return time.perf_counter() - t0
-
-
-def cpu_baseline(clips=8, repeats=3):
-    from oracle import slot_oracle as O
+def ref_modules(device, dtype=None):
+    """Reference SlotAttention (savi.py:16-110) and SlotRollouter (slotformer.py:48-134), unmodified, with the
+    bench's seeded weights."""
+    import torch
+    from oracle.build_ref import import_ref
+    R = import_ref()
     sa_w, ro_w = make_weights()
-    pe = O.sin_pos_enc(WL['T_in'], WL['d'], np.float32)
-    cpu_sample_step(sa_w, ro_w, pe, 1)
-    ts = [cpu_sample_step(sa_w, ro_w, pe, clips) for _ in range(repeats)]
+    sa = R['SlotAttention'](in_features=WL['C'], num_iterations=WL['iters'], num_slots=WL['K'], slot_size=WL['D'],
+                            mlp_hidden_size=WL['Dm'])
+    sa.load_state_dict({k: torch.from_numpy(v) for k, v in sa_w.items()}, strict=True)
+    ro = R['SlotRollouter'](num_slots=WL['K'], slot_size=WL['D'], history_len=WL['T_in'], d_model=WL['d'],
+                            num_layers=WL['layers'], num_heads=WL['heads'], ffn_dim=WL['F'])
+    missing, unexpected = ro.load_state_dict({k: torch.from_numpy(v) for k, v in ro_w.items()}, strict=False)
+    assert not unexpected and set(missing) <= {'enc_t_pe'}
+    return sa.to(device).eval(), ro.to(device).eval()
+
+
+def ref_step(sa, ro, feats, init):
+    """One step of the workload through the reference's own code path: Slot Attention frame by frame as
+    StoSAVi.encode calls it (savi.py:393-410: [B, N, C] per time step), then SlotRollouter.forward.
+    feats [B, T_in, N, C], init [T_in, B, K, D] (the per-frame initial slots the predictor would hand over, each
+    contiguous like kernel_dist_layer's output) -> (slots [B, T_in, K, D], pred [B, T_out, K, D])."""
+    import torch
+    slots = torch.stack([sa(feats[:, t], init[t]) for t in range(feats.shape[1])], dim=1)
+    return slots, ro(slots, WL['T_out'])
+
+
+def ref_inputs(device, seed=1):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    B, T = WL['B'], WL['T_in']
+    feats = torch.randn((B, T, WL['N'], WL['C']), generator=gen)
+    feats.mul_(0.5 + 1.5 * torch.rand((B, T, WL['N'], 1), generator=gen))
+    init = torch.randn((T, B, WL['K'], WL['D']), generator=gen)
+    return feats.to(device), init.to(device)
+
+
+def cpu_reference_times(steps, warmup):
+    """Full 64-clip steps of the unmodified reference on the host cores (fp32, eval, no_grad)."""
+    import torch
+    torch.set_num_threads(cpu_threads())          # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every core
+    sa, ro = ref_modules('cpu')
+    feats, init = ref_inputs('cpu')
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            ref_step(sa, ro, feats, init)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def cpu_baseline(repeats=2):
+    ts = cpu_reference_times(repeats, 1)
     t = float(np.median(ts))
-    fps = clips * (WL['T_in'] + WL['T_out']) / t
-    return {'value': fps, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
-            'sample': f'{clips} of {WL["B"]} clips ({clips * WL["T_in"]} frames SA + {clips}-clip rollout), '
-                      f'numpy oracle fp32, median of {repeats}, {t:.2f} s per sample'}
+    return {'value': frames_per_step() / t, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'reference',
+            'sample': f'the full step ({WL["B"]} clips: {WL["B"] * WL["T_in"]} frames of Slot Attention + {WL["B"]}-clip rollout) '
+                      f'through the unmodified reference modules (oracle/_ref), torch {_torch_version()} CPU fp32, '
+                      f'median of {repeats} after 1 warm-up, {t:.2f} s per step'}
+
+
+def _torch_version():
+    import torch
+    return torch.__version__
+
+
+def gpu_eager_baseline(dev, reps=10):
+    """The unmodified reference modules on the same B200 (eval, no_grad): PyTorch eager fp32 and bf16 autocast --
+    north_star's '>= 10x the reference single-GPU PyTorch forward' denominator."""
+    import torch
+    sa, ro = ref_modules(dev)
+    feats, init = ref_inputs(dev)
+    out = {}
+    with torch.no_grad():
+        for name, ctx in (('fp32', None), ('bf16_autocast', torch.bfloat16)):
+            def run():
+                if ctx is None:
+                    return ref_step(sa, ro, feats, init)
+                with torch.autocast('cuda', dtype=ctx):
+                    return ref_step(sa, ro, feats, init)
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize(dev)
+            ms = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                run()
+                b.record()
+                torch.cuda.synchronize(dev)
+                ms.append(a.elapsed_time(b))
+            out[name] = {'ms_per_step': float(np.median(ms)), 'value': frames_per_step() / (float(np.median(ms)) * 1e-3),
+                         'unit': UNIT}
+    out['what'] = ('unmodified reference SlotAttention (per time step, as StoSAVi.encode) + SlotRollouter on this GPU, '
+                   f'torch {torch.__version__} eager, eval / no_grad, device-resident inputs, median of {reps}')
+    del sa, ro, feats, init
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation (oracle port; the reference itself is Python and
-    cannot travel to the GPU box) on the host cores, bounded sample per step."""
+    """--impl reference: the reference's own implementation (oracle/_ref: unmodified savi.py / slotformer.py) on the
+    box's host cores; every step is the full 64-clip workload, nothing is extrapolated."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle import slot_oracle as O
-    sa_w, ro_w = make_weights()
-    pe = O.sin_pos_enc(WL['T_in'], WL['d'], np.float32)
-    clips = 4
-    for _ in range(max(1, args.warmup)):
-        cpu_sample_step(sa_w, ro_w, pe, clips)
-    ts = [cpu_sample_step(sa_w, ro_w, pe, clips) for _ in range(args.steps)]
+    ts = cpu_reference_times(args.steps, args.warmup)
     t = float(np.mean(ts))
-    fps = clips * (WL['T_in'] + WL['T_out']) / t
-    sample = (f'each step = {clips} of {WL["B"]} clips ({clips * WL["T_in"]} frames SA + {clips}-clip '
-              f'rollout) on the host, numpy oracle fp32')
+    fps = frames_per_step() / t
+    sample = (f'each step = the full workload ({WL["B"]} clips: {WL["B"] * WL["T_in"]} frames of Slot Attention + '
+              f'{WL["B"]}-clip rollout) through the unmodified reference modules, torch {_torch_version()} CPU fp32')
     line = {'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': t * 1e3 * WL['B'] / clips, 'higher_is_better': True,
+            'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'impl': 'reference',
-            'config': {'workload': WORKLOAD, 'note': 'ms_per_step extrapolated to the full 64-clip step'},
-            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
+            'config': {'workload': WORKLOAD, 'ms_min': float(np.min(ts)) * 1e3, 'ms_max': float(np.max(ts)) * 1e3},
+            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'reference',
                              'sample': sample},
             'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -304,26 +357,32 @@ def run_ours(args):
         launches = engine.launch_count() - n0 - 2 * 6          # minus the two warm-up batches inside capture()
         graph.replay()                                         # warm-up: one replay = K >= W steps
         sync_all()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         sampler = ClockSampler(local)
         sampler.start()
         t_wait = time.perf_counter()
         while not sampler.sm and sampler.err is None and time.perf_counter() - t_wait < 5.0:
             time.sleep(0.001)                                  # NVML is initialised: samples now arrive every ~2 ms
         sampler.sm.clear()
-        graph.replay()                                         # load for the clock samples before the timed replay too
-        sync_all()
-        ev[0].record()
-        graph.replay()                                         # exactly K steps
-        ev[1].record()
-        torch.cuda.synchronize(dev)
+        graph.replay()                                         # load for the clock samples before the timed replays too
+        # REPLAYS timed regions of exactly K steps each (one graph replay, barrier + synchronize on both sides, max
+        # over ranks); the line reports the median region, min / max beside it
+        REPLAYS = 5
+        regions = []
+        for _ in range(REPLAYS):
+            sync_all()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            graph.replay()                                     # exactly K steps
+            ev[1].record()
+            torch.cuda.synchronize(dev)
+            regions.append(ev[0].elapsed_time(ev[1]))
         clocks = sampler.result()
-        ms_total = ev[0].elapsed_time(ev[1])
         assert torch.isfinite(outs[-1][1]).all()
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        t = torch.tensor(regions, device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        regions = [float(x) for x in t.tolist()]
+        ms_total = float(np.median(regions))
         ms_per_step = ms_total / args.steps
         value = world * frames_per_step() / (ms_per_step * 1e-3)
 
@@ -443,9 +502,12 @@ def run_ours(args):
                              'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ro_tf / pk['tf'],
                              'ms_per_launch': ro_ms, 'flops_per_launch': ro_flops_total()},
     }
+    line['timed_regions'] = {'n': len(regions), 'steps_each': args.steps, 'ms_per_step_min': min(regions) / args.steps,
+                             'ms_per_step_median': ms_per_step, 'ms_per_step_max': max(regions) / args.steps}
     if e2e is not None:
         line['e2e'] = e2e
     if world == 1 and not args.no_cpu_baseline:
+        line['gpu_eager_baseline'] = gpu_eager_baseline(dev)
         line['cpu_baseline'] = cpu_baseline()
     print(json.dumps(line))
     if world > 1:

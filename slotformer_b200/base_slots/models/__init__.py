@@ -1,5 +1,6 @@
 from .slot_attention import SlotAttention, SlotAttentionWMask  # noqa: F401
 from .savi import StoSAVi  # noqa: F401
+from .steve import STEVE  # noqa: F401
 from .utils import get_lr, to_rgb_from_tensor, assert_shape, SoftPositionEmbed  # noqa: F401
 
 
@@ -10,9 +11,12 @@ def build_model(params):
                        slot_dict=params.slot_dict, enc_dict=params.enc_dict,
                        dec_dict=params.dec_dict, pred_dict=params.pred_dict,
                        loss_dict=params.loss_dict)
-    if params.model in ('dVAE', 'STEVE'):
+    if params.model == 'STEVE':
+        # slot-extraction half (encoder, SlotAttentionWMask, predictor); the dVAE / SLATE decoder are not built
+        return STEVE(resolution=params.resolution, clip_len=params.input_frames, slot_dict=params.slot_dict,
+                     dvae_dict=params.dvae_dict, enc_dict=params.enc_dict, dec_dict=params.dec_dict,
+                     pred_dict=params.pred_dict, loss_dict=params.loss_dict)
+    if params.model == 'dVAE':
         raise NotImplementedError(
-            f'{params.model}: the dVAE tokenizer / SLATE decoder are outside the hot-path scope '
-            '(SURVEY.md section 2, rows 11-13); use SlotAttentionWMask directly for the STEVE '
-            'slot-extraction path.')
+            'dVAE: the image tokenizer is a different model, outside the hot-path scope (SURVEY.md section 2, row 12).')
     raise NotImplementedError(f'{params.model} is not implemented.')

@@ -2,6 +2,7 @@ from .rollouter import (Rollouter, SlotRollouter, SingleStepSlotRollouter,  # no
                         get_sin_pos_enc, build_pos_enc)
 from .slotformer import SlotFormer  # noqa: F401
 from .single_step_slotformer import SingleStepSlotFormer  # noqa: F401
+from .steve_slotformer import STEVESlotFormer  # noqa: F401
 
 
 def build_model(params):
@@ -14,7 +15,6 @@ def build_model(params):
     if params.model == 'SingleStepSlotFormer':
         return SingleStepSlotFormer(**kwargs)
     if params.model == 'STEVESlotFormer':
-        raise NotImplementedError(
-            'STEVESlotFormer needs the dVAE / SLATE decoder, which is outside the hot-path scope '
-            '(SURVEY.md section 2, rows 9, 12, 13); its rollout is the same SlotRollouter.')
+        # rollout only: the dVAE / token decoder are not built (steve_slotformer.py:105-109 is the whole rollout)
+        return STEVESlotFormer(dvae_dict=params.dvae_dict, **kwargs)
     raise NotImplementedError(f'{params.model} is not implemented.')

@@ -64,8 +64,9 @@ def test_build_model_with_every_reference_config():
         for path in sorted(glob.glob(f'{REF}/video_prediction/configs/slotformer_*_params*.py')):
             params = load(path)
             if params.model == 'STEVESlotFormer':
-                with pytest.raises(NotImplementedError):
-                    video_prediction.build_model(params)
+                model = video_prediction.build_model(params)          # rollout only: no dVAE / decoder checkpoint needed
+                assert model.rollouter.history_len == params.rollout_dict['history_len'] and model.decoder is None
+                built += 1
                 continue
             key = (tuple(params.resolution), params.slot_dict['slot_size'], tuple(params.dec_dict['dec_channels']),
                    tuple(params.dec_dict['dec_resolution']))
@@ -74,7 +75,13 @@ def test_build_model_with_every_reference_config():
             model = video_prediction.build_model(params)
             assert model.rollouter.history_len == params.rollout_dict['history_len']
             built += 1
-    assert built >= 6
+        for path in sorted(glob.glob(f'{REF}/base_slots/configs/steve_*_params*.py')):
+            params = load(path)
+            assert params.model == 'STEVE'
+            model = base_slots.build_model(params)                    # slot-extraction half, no dVAE checkpoint needed
+            assert type(model.slot_attention).__name__ == 'SlotAttentionWMask'
+            built += 1
+    assert built >= 8
 
 
 @pytest.mark.gpu
@@ -166,3 +173,57 @@ def test_savi_frame_loop_cuda_graph_matches_eager():
         new = both(img2, True)
         assert all(torch.equal(a, b) for a, b in zip(both(img2, False), new))
         assert not torch.equal(new[1], got[1])
+
+
+def _steve_gold():
+    return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'steve.npz'))
+
+
+def test_steve_callers_keep_reference_state_dict_keys():
+    """STEVE (slot extraction) and STEVESlotFormer (rollout only) build everything the reference builds apart from
+    the dVAE / token decoder, under the reference's state_dict keys; a reference checkpoint loads strictly once its
+    dvae.* / trans_decoder.* / decoder.* entries are dropped (which load_state_dict does)."""
+    from slotformer_b200.base_slots.models import STEVE
+    from slotformer_b200.video_prediction.models import STEVESlotFormer
+    g = _steve_gold()
+    m = W.build_steve(STEVE)
+    assert sorted(m.state_dict().keys()) == sorted(g['steve_keys'].tolist())
+    sd = dict(m.state_dict())
+    sd['dvae.encoder.0.weight'] = torch.zeros(1)
+    sd['trans_decoder.head.weight'] = torch.zeros(1)
+    m.load_state_dict(sd, strict=True)
+    sf = W.build_steve_slotformer(STEVESlotFormer)
+    assert sorted(sf.state_dict().keys()) == sorted(g['ssf_keys'].tolist())
+    with pytest.raises(NotImplementedError):
+        sf.decode(torch.zeros(1, 6, 192))
+
+
+@pytest.mark.gpu
+def test_steve_extraction_matches_reference_on_gpu():
+    """BASELINE config 4 caller: STEVE.encode through SlotAttentionWMask (C = D = 192, masks up-sampled to 128x128)."""
+    from slotformer_b200.base_slots.models import STEVE
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = _steve_gold()
+    m = W.build_steve(STEVE).cuda()
+    img = W.steve_input().cuda()
+    with torch.no_grad():
+        out = m({'img': img})
+    assert set(out) == {'slots', 'masks'}
+    assert out['masks'].shape == (2, 3, 6, 128, 128)
+    assert rel_max(out['slots'].cpu().numpy(), g['steve_slots']) < 2e-3
+    assert np.abs(out['masks'].cpu().numpy()[..., 1::4, 2::4] - g['steve_masks_sub']).max() < 2e-3
+
+
+@pytest.mark.gpu
+def test_steve_slotformer_rollout_matches_reference_on_gpu():
+    from slotformer_b200.video_prediction.models import STEVESlotFormer
+    g = _steve_gold()
+    m = W.build_steve_slotformer(STEVESlotFormer).cuda()
+    x = W.steve_slotformer_input().cuda()
+    with torch.no_grad():
+        fwd = m({'slots': x})
+        loss = m.calc_train_loss({'slots': x}, fwd)
+    assert rel_max(fwd['pred_slots'].cpu().numpy(), g['ssf_pred']) < 4e-3
+    assert torch.equal(fwd['gt_slots'], x[:, 6:])
+    assert abs(loss['slot_recon_loss'].item() - float(g['ssf_loss'])) < 1e-2 * float(g['ssf_loss'])
