@@ -82,7 +82,12 @@ def main():
     total = args.synthetic_steps
     warmup = max(1, int(total * params.get('warmup_steps_pct', 0.025)))
     gen = torch.Generator(device=device).manual_seed(1 + args.local_rank)
+    from slotformer_b200 import engine
+    n_launch0 = engine.launch_count()
+    ar_ms, step_ms, payload = [], [], 0
     for step in range(total):
+        t_step = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_step[0].record()
         for g in opt.param_groups:
             g['lr'] = lr_at(step, total, warmup, params.lr)
         batch = synthetic_batch(args.task, params, model, device, gen)
@@ -95,14 +100,33 @@ def main():
         scaler.unscale_(opt)
         if args.ddp:
             from slotformer_b200.parallel import allreduce_gradients
-            allreduce_gradients(model)
+            t_ar = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_ar[0].record()
+            payload = allreduce_gradients(model) * 4               # ONE flattened NCCL all-reduce (fp32)
+            t_ar[1].record()
         if params.get('clip_grad', -1) > 0:
             torch.nn.utils.clip_grad_norm_(trainable, params.clip_grad)
         scaler.step(opt)
         scaler.update()
+        t_step[1].record()
+        torch.cuda.synchronize(device)
+        step_ms.append(t_step[0].elapsed_time(t_step[1]))
+        if args.ddp:
+            ar_ms.append(t_ar[0].elapsed_time(t_ar[1]))
         if args.local_rank == 0 and (step % 5 == 0 or step == total - 1):
             print(f'step {step:4d}  loss {loss.item():.5f}  ' +
                   '  '.join(f'{k} {v.item():.5f}' for k, v in losses.items()), flush=True)
+    if args.local_rank == 0:
+        import json
+        import statistics
+        summary = {'task': args.task, 'params': os.path.basename(args.params), 'steps': total,
+                   'world_size': int(os.environ.get('WORLD_SIZE', 1)),
+                   'ms_per_step_median': statistics.median(step_ms[2:] or step_ms),
+                   'kernel_launches_per_step': (engine.launch_count() - n_launch0) / total}
+        if ar_ms:
+            summary.update(allreduce_payload_bytes=payload, allreduce_ms_median=statistics.median(ar_ms[2:] or ar_ms),
+                           allreduce_ms_min=min(ar_ms[2:] or ar_ms), allreduce_backend='nccl')
+        print('TRAIN_SUMMARY ' + json.dumps(summary), flush=True)
     if args.out and args.local_rank == 0:
         torch.save({'state_dict': model.state_dict(), 'it': total}, args.out)
     if args.ddp:

@@ -8,6 +8,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from ...autograd import KernelForward
 from ...engine import SA_WEIGHT_KEYS, SlotAttentionEngine
 
 
@@ -72,16 +73,26 @@ class SlotAttention(nn.Module):
             slots = slots + self.mlp(slots)
         return (slots, mask) if return_mask else slots
 
-    def _run(self, inputs, slots, return_mask):
-        assert inputs.dim() == 3 and slots.dim() == 3
-        if self._needs_autograd(inputs, slots):
-            return self._autograd_forward(inputs, slots, return_mask)
+    def _kernel(self, inputs, slots, return_mask):
         return self._engine.forward(
             inputs.detach() if inputs.dtype == torch.bfloat16 else inputs.detach().float(),
             slots.detach().float(),
             {k: v.detach() for k, v in self._weights().items()},
             self.num_iterations, self.eps, self.mlp_hidden_size, return_mask=return_mask,
             chunk_frames=self.chunk_frames, max_ctas=self.max_ctas, flags=self.engine_flags)
+
+    def _run(self, inputs, slots, return_mask):
+        assert inputs.dim() == 3 and slots.dim() == 3
+        if not self._needs_autograd(inputs, slots):
+            return self._kernel(inputs, slots, return_mask)
+        if not inputs.is_cuda:
+            return self._autograd_forward(inputs, slots, return_mask)      # CPU autograd (unit tests of the wrappers)
+        # gradients required: the FORWARD still runs on the sm_100a kernels; the backward recomputes the operator
+        # with the differentiable restatement (slotformer_b200/autograd.py)
+        params = list(self._weights().values())
+        return KernelForward.apply(lambda i, s: self._kernel(i, s, return_mask),
+                                   lambda i, s: self._autograd_forward(i, s, return_mask),
+                                   2, 1, inputs, slots, *params)
 
     def forward(self, inputs, slots):
         """inputs [B, N, C] flattened per-pixel features; slots [B, K, D] initial slots.

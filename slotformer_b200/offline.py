@@ -149,3 +149,52 @@ def extract_video_slots(model, get_video, names, batch_videos=8, device='cuda:0'
         pending.append((n, v))
     flush()
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# PHYRE extraction: job-level sharding + resume (extract_phyre_slots.py:41-76, scripts/parallel_phyre.sh:22-28)
+# ----------------------------------------------------------------------------------------------
+def phyre_split_range(total_num, split, total_split):
+    """Sample range [start, end) of job ``split`` of ``total_split`` (extract_phyre_slots.py:41-44): equal shares of
+    ``total_num // total_split``, the last job takes the remainder; ``split == -1`` is the whole set."""
+    if split == -1:
+        return 0, total_num
+    if not 0 <= split < total_split:
+        raise ValueError(f'split {split} outside [0, {total_split})')
+    share = total_num // total_split
+    return share * split, (share * (split + 1) if split < total_split - 1 else total_num)
+
+
+def phyre_resume_start(save_root, start_idx, end_idx):
+    """First sample this job still has to do (extract_phyre_slots.py:45-53): scan for the first missing
+    ``{idx:06d}.npy`` and go back by one, "in case the last file is corrupted".  The reference clamps at 0
+    (`max(idx - 1, 0)`), so a fresh job re-writes the last file of its neighbour; here the clamp is the job's own
+    start, which keeps concurrently running jobs from touching each other's files."""
+    idx = start_idx
+    for idx in range(start_idx, end_idx):
+        if not os.path.exists(os.path.join(save_root, f'{idx:06d}.npy')):
+            break
+    return max(idx - 1, start_idx)
+
+
+@torch.no_grad()
+def extract_phyre_job(model, get_sample, total_num, save_root, split=-1, total_split=1, batch_size=8,
+                      device='cuda:0', slot_key='post_slots', resume=True):
+    """One shard of the PHYRE extraction job.  ``get_sample(idx) -> (video float [T, 3, H, W], vid_len)``; every
+    sample's slots are saved to ``save_root/{idx:06d}.npy`` cut to its real length.  Jobs are independent (one per GPU
+    / Slurm job, no collective); a restarted job skips what it already wrote.  Returns the indices written."""
+    model.eval()
+    os.makedirs(save_root, exist_ok=True)
+    start, end = phyre_split_range(total_num, split, total_split)
+    if split != -1 and resume:
+        start = phyre_resume_start(save_root, start, end)
+    written = []
+    for b0 in range(start, end, batch_size):
+        idxs = list(range(b0, min(b0 + batch_size, end)))
+        samples = [get_sample(i) for i in idxs]
+        vids = torch.stack([torch.as_tensor(v) for v, _ in samples]).float().to(device)
+        slots = model({'img': vids})[slot_key].detach().float().cpu().numpy()
+        for i, (_, vid_len), s in zip(idxs, samples, slots):
+            save_phyre_sample(save_root, i, s, vid_len)
+            written.append(i)
+    return written

@@ -8,6 +8,7 @@ arguments, same parameter names (``in_proj``, ``transformer_encoder.layers.<i>.*
 import torch
 from torch import nn
 
+from ...autograd import KernelForward, warn_once
 from ...engine import RolloutEngine
 
 
@@ -128,7 +129,23 @@ class SlotRollouter(Rollouter):
         if not self.norm_first:
             raise NotImplementedError('the sm_100a engine implements the pre-LN encoder only')
         if self._needs_autograd(x):
-            return self._autograd_forward(x, pred_len)
+            dropout = self.training and any(m.p > 0 for m in self.modules() if isinstance(m, nn.Dropout))
+            if dropout or not x.is_cuda:
+                # train() mode: nn.TransformerEncoderLayer's dropout (p = 0.1, slotformer.py:72-78) is part of the
+                # reference's training forward and is not in the kernel -> the differentiable restatement runs
+                if dropout and x.is_cuda:
+                    warn_once('ro_dropout', 'SlotRollouter in train() mode with dropout > 0: the forward pass runs the '
+                              'PyTorch restatement, not the sm_100a kernel (call .eval() or set dropout to 0 to train '
+                              'on the kernel forward)')
+                return self._autograd_forward(x, pred_len)
+            # gradients required, no dropout: FORWARD on the kernel, backward through the restatement
+            params = [p for n, p in self.named_parameters()
+                      if n.startswith(('in_proj.', 'out_proj.', 'transformer_encoder.')) or n in ('enc_t_pe', 'enc_slots_pe')]
+            return KernelForward.apply(lambda h: self._kernel(h, pred_len), lambda h: self._autograd_forward(h, pred_len),
+                                       1, 1, x, *params)
+        return self._kernel(x, pred_len)
+
+    def _kernel(self, x, pred_len):
         return self._engine.forward(
             x.detach().float(), self._weights(), self._token_pe().detach().float(),
             self.num_layers, self.num_heads, pred_len, mode=self._mode,

@@ -5,8 +5,9 @@ Tolerances (stated per BASELINE.json north_star, 'within 1e-3 rel'): metric is
 max|out-ref| / max|ref| (helpers.rel_max).
   * Slot Attention slots           <= 1e-3  (fp16 tensor-core operands, fp32 everything else)
   * Slot Attention seg mask        <= 2e-3  absolute (mask values are probabilities in [0,1])
-  * rollout, first predicted step  <= 1.5e-3
-  * rollout, free running <=64 steps <= 4e-3 (error compounds through the autoregression)
+  * rollout, one step from exact inputs (first step and every teacher-forced step)  <= 1e-3
+  * rollout, free running: step s (0-based) <= 1e-3 * (1 + 0.05 s), i.e. 1e-3 at the first step growing to 4.2e-3
+    at step 63 (the fed-back slots carry the earlier steps' error through the autoregression)
 """
 import numpy as np
 import pytest
@@ -19,6 +20,18 @@ from slotformer_b200 import engine
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
+STEP_TOL = 1e-3
+
+
+def free_running_tol(step):
+    return STEP_TOL * (1. + 0.05 * step)
+
+
+def assert_rollout_close(out, ref):
+    """Per-step relative error of a free-running rollout against the stated bound."""
+    for s in range(ref.shape[1]):
+        e = rel_max(out[:, s], ref[:, s])
+        assert e < free_running_tol(s), (s, e, free_running_tol(s))
 
 
 @pytest.mark.parametrize('name', list(cases.SA_CASES))
@@ -112,8 +125,40 @@ def test_rollout_vs_reference_golden(name):
         out = m(torch.from_numpy(hist).to(DEV), c['pred_len']).cpu().numpy()
     ref = g['pred_f64']
     assert out.shape == ref.shape
-    assert rel_max(out[:, 0], ref[:, 0]) < 1.5e-3
-    assert rel_max(out, ref) < 4e-3
+    assert_rollout_close(out, ref)
+
+
+@pytest.mark.parametrize('name', list(cases.RO_CASES))
+def test_rollout_teacher_forced_every_step(name):
+    """Per-step error separated from compounding: step s is predicted from the REFERENCE's own window (burn-in slots +
+    the golden predictions before s, exact inputs) and must match the golden step s within 1e-3 -- all steps of every
+    golden case, 64 of them for ro_cfg5.  A growing-window step with w frames in the window equals a sliding-window
+    rollouter of history_len w (the positional rows are the last w rows of the table: single_step_slotformer.py:81)."""
+    from slotformer_b200.video_prediction.models import SlotRollouter
+    c, w, hist = cases.ro_case(name)
+    g = golden(name)
+    ref = g['pred_f64']
+    seq = np.concatenate([hist.astype(np.float64), ref], axis=1)          # [B, T_h + pred_len, K, Ds]
+    T_h, wmax = c['T_h'], (c['cond_len'] if c['mode'] == 'grow' else c['T_h'])
+    by_w = {}
+    for s in range(c['pred_len']):
+        by_w.setdefault(min(T_h + s, wmax), []).append(s)
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    worst = 0.
+    for wlen, steps in by_w.items():
+        m = SlotRollouter(num_slots=c['K'], slot_size=c['Ds'], history_len=wlen, d_model=c['d'],
+                          num_layers=c['layers'], num_heads=c['heads'], ffn_dim=c['F'])
+        m.load_state_dict(sd, strict=False)
+        m = m.to(DEV).eval()
+        x = np.concatenate([seq[:, T_h + s - wlen:T_h + s] for s in steps], axis=0).astype(np.float32)
+        with torch.no_grad():
+            out = m(torch.from_numpy(x).to(DEV), 1).cpu().numpy()[:, 0]
+        out = out.reshape(len(steps), -1, c['K'], c['Ds'])
+        for i, s in enumerate(steps):
+            e = rel_max(out[i], ref[:, s])
+            worst = max(worst, e)
+            assert e < STEP_TOL, (name, s, e)
+    assert worst > 0.
 
 
 @pytest.mark.parametrize('name', ['ro_tiny', 'ro_pack'])
@@ -170,7 +215,7 @@ def test_rollout_baseline_configs_full_batch(name, B):
         assert torch.equal(a, m(x, c['pred_len']))
         sub = m(x[[B - 1, 1]].contiguous(), c['pred_len'])
     assert torch.equal(sub, a[[B - 1, 1]])
-    assert rel_max(a[:hist.shape[0]].cpu().numpy(), g['pred_f64']) < 4e-3
+    assert_rollout_close(a[:hist.shape[0]].cpu().numpy(), g['pred_f64'])
 
 
 def test_engine_rejects_cpu_tensors_and_bad_shapes():
@@ -235,7 +280,7 @@ def test_rollout_mma_engine_matches_tcgen05_engine_and_repeats():
         a = m(x, c['pred_len'])
         for _ in range(3):
             assert torch.equal(a, m(x, c['pred_len']))
-    assert rel_max(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < 4e-3
+    assert rel_max(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < free_running_tol(c['pred_len'] - 1)
 
 
 @pytest.mark.parametrize('K,N', [(8, 1000), (8, 4096), (7, 520), (1, 4096)])

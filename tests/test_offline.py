@@ -100,3 +100,43 @@ def test_offline_rollout_with_kernel_matches_oracle():
             hist = pre[n][24 - 12 + o::2][:6][None]
             ref = O.rollout(hist, w2, 5, c['heads'], c['layers'])[0]
             assert rel_max(res[n][24 + o::2], ref) < 4e-3
+
+
+def test_phyre_split_ranges_and_resume(tmp_path):
+    """extract_phyre_slots.py:41-53 arithmetic: equal shares, the last job takes the remainder; a restarted job
+    re-does the last file it wrote and skips the rest."""
+    total, n = 103, 8
+    ranges = [offline.phyre_split_range(total, s, n) for s in range(n)]
+    assert ranges[0] == (0, 12) and ranges[-1] == (84, 103)
+    assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))          # contiguous, disjoint, complete
+    assert offline.phyre_split_range(total, -1, n) == (0, total)
+    with pytest.raises(ValueError):
+        offline.phyre_split_range(total, 8, 8)
+
+    class FakeSavi(torch.nn.Module):
+        testing = True
+
+        def forward(self, d):               # [B, T, 3, H, W] -> post_slots [B, T, 2, 4] = per-frame pixel mean + slot id
+            m = d['img'].mean(dim=(2, 3, 4))
+            return {'post_slots': m[:, :, None, None] + torch.arange(2.)[None, None, :, None] + torch.zeros(4)}
+
+    def get_sample(i):
+        return np.full((5, 3, 4, 4), float(i), dtype=np.float32), 3 + i % 3
+
+    root = str(tmp_path / 'slots')
+    calls = []
+
+    def counting(i):
+        calls.append(i)
+        return get_sample(i)
+
+    wrote = offline.extract_phyre_job(FakeSavi(), counting, 20, root, split=1, total_split=3, batch_size=4, device='cpu')
+    assert wrote == list(range(6, 12))
+    for i in wrote:
+        s = np.load(os.path.join(root, f'{i:06d}.npy'))
+        assert s.dtype == np.float32 and s.shape == (3 + i % 3, 2, 4) and np.allclose(s[:, 1], i + 1)
+    os.remove(os.path.join(root, '000010.npy'))                # simulate a job killed after sample 9
+    os.remove(os.path.join(root, '000011.npy'))
+    calls.clear()
+    wrote = offline.extract_phyre_job(FakeSavi(), counting, 20, root, split=1, total_split=3, batch_size=4, device='cpu')
+    assert wrote == [9, 10, 11] and calls == [9, 10, 11]
