@@ -198,11 +198,12 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
  *                  the frame's background slot (smallest per-slot maximum) takes every pixel whose best score is
  *                  below fg_thre, then argmax over slots (first maximum, as torch.argmax)
  *   slot_max_ws    B*K uint32 of scratch, required iff seg != NULL
- * Supported: 1 <= K <= 12, HW % 4 == 0, B <= 65535. */
+ *                  (scores of any sign: the per-slot maxima use an order-preserving integer encoding)
+ * Supported: 1 <= K <= 12, HW % 4 == 0; any B (batches beyond 65535 frames are sliced internally). */
 int sfb_decode_combine(const float* dec_out, float* masks, float* recon_combined, long long* seg,
                        void* slot_max_ws, int B, int K, int HW, float fg_thre, void* stream);
 
-/* postproc_mask on given masks [B, K, HW] (vp_utils.py:20-41) -> seg [B, HW] int64.  K <= 16, B*K <= 65535. */
+/* postproc_mask on given masks [B, K, HW] (vp_utils.py:20-41) -> seg [B, HW] int64.  K <= 16, any B. */
 int sfb_postproc_mask(const float* masks, long long* seg, void* slot_max_ws, int B, int K, int HW, float fg_thre,
                       void* stream);
 

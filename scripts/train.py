@@ -60,6 +60,10 @@ def main():
     ap.add_argument('--local_rank', '--local-rank', type=int, default=int(os.environ.get('LOCAL_RANK', 0)))
     ap.add_argument('--synthetic-steps', type=int, default=20)
     ap.add_argument('--out', type=str, default='')
+    ap.add_argument('--synthetic-decoder', action='store_true',
+                    help='video_prediction: mint the frozen SAVi decoder checkpoint from a fresh initialisation')
+    ap.add_argument('--eval-mode-forward', action='store_true',
+                    help='keep the model in eval() (no dropout): the rollout forward then runs on the kernel too')
     args = ap.parse_args()
 
     task = importlib.import_module(f'slotformer_b200.{args.task}')
@@ -72,10 +76,26 @@ def main():
     if args.ddp:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
+    if args.synthetic_decoder and not params.dec_dict.get('dec_ckp_path'):
+        import tempfile
+        from slotformer_b200.base_slots.models.savi import build_broadcast_decoder
+
+        class _Dec(torch.nn.Module):
+            pass
+        torch.manual_seed(0)
+        owner = _Dec()
+        owner.dec_dict, owner.slot_size, owner.resolution = params.dec_dict, params.slot_dict['slot_size'], params.resolution
+        build_broadcast_decoder(owner)
+        path = os.path.join(tempfile.gettempdir(), f'sfb_synth_decoder_{os.getpid()}.pth')
+        torch.save({'state_dict': owner.state_dict()}, path)
+        params.dec_dict = dict(params.dec_dict, dec_ckp_path=path)
+    torch.manual_seed(0)                                       # identical initial replicas on every rank
     model = task.build_model(params).to(device)
     if args.weight:
         model.load_state_dict(torch.load(args.weight, map_location='cpu')['state_dict'])
     model.train()
+    if args.eval_mode_forward:
+        model.eval()
     trainable = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(trainable, lr=params.lr)
     scaler = torch.amp.GradScaler('cuda', enabled=args.fp16)

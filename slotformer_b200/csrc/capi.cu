@@ -366,7 +366,6 @@ int sfb_decode_combine(const float* dec_out, float* masks, float* recon_combined
     if (!dec_out || !masks || !recon_combined) return SFB_E_NULL;
     if (seg && !slot_max_ws) return SFB_E_NULL;
     if (B < 0 || K < 1 || K > 12 || HW < 4 || (HW & 3)) return SFB_E_BAD_SHAPE;
-    if (B > 65535) return SFB_E_BAD_SHAPE;
     if (!aligned16(dec_out) || !aligned16(masks) || !aligned16(recon_combined)) return SFB_E_BAD_ALIGN;
     DevInfo di;
     int rc = device_info(&di);
@@ -379,13 +378,20 @@ int sfb_decode_combine(const float* dec_out, float* masks, float* recon_combined
         e = cudaMemsetAsync(smax, 0, (size_t)B * K * sizeof(unsigned int), st);
         if (e != cudaSuccess) return cuda_err(e);
     }
-    e = sfb::decode_combine_launch(dec_out, masks, recon_combined, smax, B, K, HW, di.sms, st);
-    if (e != cudaSuccess) return cuda_err(e);
-    g_launches.fetch_add(1);
-    if (seg) {
-        e = sfb::seg_argmax_launch(masks, smax, seg, B, K, HW, fg_thre, di.sms, st);
+    // frames sit on gridDim.y (<= 65535): larger batches go in slices
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        const size_t px = (size_t)b0 * HW;
+        unsigned int* sm = smax ? smax + (size_t)b0 * K : nullptr;
+        e = sfb::decode_combine_launch(dec_out + px * K * 4, masks + px * K, recon_combined + px * 3, sm, nb, K, HW,
+                                       di.sms, st);
         if (e != cudaSuccess) return cuda_err(e);
         g_launches.fetch_add(1);
+        if (seg) {
+            e = sfb::seg_argmax_launch(masks + px * K, sm, seg + px, nb, K, HW, fg_thre, di.sms, st);
+            if (e != cudaSuccess) return cuda_err(e);
+            g_launches.fetch_add(1);
+        }
     }
     return SFB_OK;
 }
@@ -394,7 +400,7 @@ int sfb_postproc_mask(const float* masks, long long* seg, void* slot_max_ws, int
                       void* stream) {
     if (B == 0) return SFB_OK;
     if (!masks || !seg || !slot_max_ws) return SFB_E_NULL;
-    if (B < 0 || B > 65535 || K < 1 || K > 16 || HW < 1 || (long long)B * K > 65535) return SFB_E_BAD_SHAPE;
+    if (B < 0 || K < 1 || K > 16 || HW < 1) return SFB_E_BAD_SHAPE;
     DevInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
@@ -403,9 +409,16 @@ int sfb_postproc_mask(const float* masks, long long* seg, void* slot_max_ws, int
     unsigned int* smax = reinterpret_cast<unsigned int*>(slot_max_ws);
     cudaError_t e = cudaMemsetAsync(smax, 0, (size_t)B * K * sizeof(unsigned int), st);
     if (e != cudaSuccess) return cuda_err(e);
-    if ((e = sfb::mask_max_launch(masks, smax, B * K, HW, di.sms, st)) != cudaSuccess) return cuda_err(e);
-    if ((e = sfb::seg_argmax_launch(masks, smax, seg, B, K, HW, fg_thre, di.sms, st)) != cudaSuccess) return cuda_err(e);
-    g_launches.fetch_add(2);
+    // (frame, slot) planes / frames sit on gridDim.y (<= 65535): larger batches go in slices of whole frames
+    const int fmax = 65535 / K;
+    for (int b0 = 0; b0 < B; b0 += fmax) {
+        const int nb = (B - b0) < fmax ? (B - b0) : fmax;
+        const size_t px = (size_t)b0 * HW;
+        if ((e = sfb::mask_max_launch(masks + px * K, smax + (size_t)b0 * K, nb * K, HW, di.sms, st)) != cudaSuccess) return cuda_err(e);
+        if ((e = sfb::seg_argmax_launch(masks + px * K, smax + (size_t)b0 * K, seg + px, nb, K, HW, fg_thre, di.sms, st)) != cudaSuccess)
+            return cuda_err(e);
+        g_launches.fetch_add(2);
+    }
     return SFB_OK;
 }
 

@@ -16,6 +16,17 @@
 
 namespace sfb {
 
+// Order-preserving float <-> uint32 map (any sign): u(a) < u(b) <=> a < b, and 0 is below every encoded value, so a
+// zero-filled word is the identity of atomicMax.  postproc_mask accepts arbitrary scores, not only probabilities.
+__device__ __forceinline__ unsigned int ord_enc(float v) {
+    const unsigned int b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord_dec(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+
 static constexpr int DC_THREADS = 256;
 static constexpr int DC_MAXK = 16;
 
@@ -68,7 +79,7 @@ __global__ void __launch_bounds__(DC_THREADS) decode_combine_kernel(const float*
             float v = vmax[k];
 #pragma unroll
             for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if ((threadIdx.x & 31) == 0) atomicMax(slot_max + (size_t)b * K + k, __float_as_uint(v));   // v >= 0
+            if ((threadIdx.x & 31) == 0) atomicMax(slot_max + (size_t)b * K + k, ord_enc(v));
         }
     }
 }
@@ -77,11 +88,11 @@ __global__ void __launch_bounds__(DC_THREADS) decode_combine_kernel(const float*
 __global__ void __launch_bounds__(DC_THREADS) mask_max_kernel(const float* __restrict__ masks, unsigned int* __restrict__ slot_max,
                                                               int HW) {
     const float* mk = masks + (size_t)blockIdx.y * HW;
-    float v = 0.f;
+    float v = -INFINITY;
     for (int i = blockIdx.x * DC_THREADS + threadIdx.x; i < HW; i += gridDim.x * DC_THREADS) v = fmaxf(v, __ldg(mk + i));
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(slot_max + blockIdx.y, __float_as_uint(v));
+    if ((threadIdx.x & 31) == 0) atomicMax(slot_max + blockIdx.y, ord_enc(v));
 }
 
 // one thread per pixel: first-occurrence argmin / argmax exactly as torch.argmin / torch.argmax define them
@@ -91,9 +102,9 @@ __global__ void __launch_bounds__(DC_THREADS) seg_argmax_kernel(const float* __r
     __shared__ int bg_s;
     if (threadIdx.x == 0) {
         int bg = 0;
-        float best = __uint_as_float(slot_max[(size_t)b * K]);
+        float best = ord_dec(slot_max[(size_t)b * K]);
         for (int k = 1; k < K; ++k) {
-            const float v = __uint_as_float(slot_max[(size_t)b * K + k]);
+            const float v = ord_dec(slot_max[(size_t)b * K + k]);
             if (v < best) { best = v; bg = k; }
         }
         bg_s = bg;

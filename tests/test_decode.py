@@ -88,3 +88,18 @@ def test_decode_rejects_bad_input():
         engine.decode_combine(torch.zeros((1, 3, 3, 4, 4), device='cuda'))   # 3 planes
     r, m = engine.decode_combine(torch.zeros((0, 3, 4, 4, 4), device='cuda'))
     assert r.shape == (0, 3, 4, 4) and m.shape == (0, 3, 1, 4, 4)
+
+
+@pytest.mark.gpu
+def test_postproc_mask_large_batches_and_negative_scores():
+    """More (frame, slot) planes than one grid dimension holds (64 x 160 x 7 = 71680 > 65535) and scores of either
+    sign (postproc_mask takes arbitrary scores, vp_utils.py:20-41): bit-exact against the oracle."""
+    from slotformer_b200 import engine
+    gen = torch.Generator(device='cuda').manual_seed(9)
+    m = torch.randn((64, 160, 7, 1, 8, 8), device='cuda', generator=gen)          # mostly below the 0.5 threshold
+    seg = engine.postproc_mask(m)
+    assert seg.shape == (64, 160, 8, 8)
+    ref = O.postproc_mask(m.cpu().numpy())
+    assert np.array_equal(seg.cpu().numpy(), ref)
+    neg = -torch.rand((3, 2, 4, 1, 4, 4), device='cuda', generator=gen) - 0.1      # every score negative
+    assert np.array_equal(engine.postproc_mask(neg).cpu().numpy(), O.postproc_mask(neg.cpu().numpy()))
