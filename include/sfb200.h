@@ -43,6 +43,7 @@ extern "C" {
 
 #define SFB_DTYPE_F32 0
 #define SFB_DTYPE_BF16 1
+#define SFB_DTYPE_TILES16 2 /* pre-normalised fp16 operand tiles written by sfb_enc_tail_forward (C = 128) */
 
 #define SFB_RO_SLIDE 0 /* SlotRollouter: fixed window, drop oldest frame each step       */
 #define SFB_RO_GROW 1  /* SingleStepSlotRollouter: window grows up to cond_len frames    */
@@ -110,7 +111,10 @@ int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspac
 
 /* Slot Attention forward for B independent frames (after sfb_sa_prepare on the same workspace).
  *   feats        [B, N, C]  fp32 (SFB_DTYPE_F32) or bf16 (SFB_DTYPE_BF16); rows contiguous, frame b at
- *                feats + b*feat_batch_stride elements (savi.py:406 passes encoder_out[:, idx])
+ *                feats + b*feat_batch_stride elements (savi.py:406 passes encoder_out[:, idx]);
+ *                or, with SFB_DTYPE_TILES16, the tiles of sfb_enc_tail_forward (frame b at feats +
+ *                b*feat_batch_stride fp16 elements): the features are then already LayerNorm-ed operand
+ *                tiles and every iteration streams them straight into the tensor cores
  *   slots_in     [B, K, D]  fp32 initial slots          slots_out [B, K, D] fp32
  *   seg_mask     NULL, or [B, K, N] fp32: softmax-over-slots attention of the LAST iteration,
  *                before +eps / renormalisation (steve.py:54-55)
@@ -128,6 +132,35 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                    const sfb_sa_weights* w, int B, int N, int C, int D, int Dm, int K,
                    int n_iter, float eps, int chunk_frames, int max_ctas, unsigned int flags,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Encoder tail (next row f1): CNN output -> Slot Attention operand tiles     */
+/* ------------------------------------------------------------------------- */
+/* StoSAVi._get_encoder_out after the CNN (base_slots/models/savi.py:371-377, utils.py:52-63) fused with
+ * SlotAttention.norm_inputs (savi.py:66):  + SoftPositionEmbed -> LayerNorm(64) -> Linear(64, C) -> ReLU ->
+ * Linear(C, C) -> LayerNorm statistics of Slot Attention, written as fp16 operand tiles.  The fp32
+ * [frames, N, C] feature grid of the reference is never materialised.  C = 128, 64 CNN channels. */
+typedef struct sfb_enc_tail_weights {
+    const float* encoder_pos_embedding_dense_weight; /* [64, 4]  */
+    const float* encoder_pos_embedding_dense_bias;   /* [64]     */
+    const float* encoder_out_layer_0_weight;         /* [64]  LayerNorm */
+    const float* encoder_out_layer_0_bias;           /* [64]     */
+    const float* encoder_out_layer_1_weight;         /* [C, 64]  */
+    const float* encoder_out_layer_1_bias;           /* [C]      */
+    const float* encoder_out_layer_3_weight;         /* [C, C]   */
+    const float* encoder_out_layer_3_bias;           /* [C]      */
+} sfb_enc_tail_weights;
+
+size_t sfb_enc_tail_workspace_bytes(int C);
+/* bytes of the tile buffer for `frames` frames of N pixels (128-pixel tiles of 32 KB; = frames * tile_frame_bytes) */
+size_t sfb_enc_tail_tiles_bytes(int frames, int N, int C);
+/* fold + pack the weights into `workspace` (call again when a weight changed) */
+int sfb_enc_tail_prepare(const sfb_enc_tail_weights* w, int C, void* workspace, size_t workspace_bytes, void* stream);
+/* cnn_out [frames, 64, H, W] fp32 (NCHW, frame f at cnn_out + f*frame_stride elements) -> tiles (frame-major,
+ * sfb_enc_tail_tiles_bytes(1, H*W, C) bytes per frame), to be passed to sfb_sa_forward as SFB_DTYPE_TILES16.
+ * max_ctas: as in sfb_sa_forward. */
+int sfb_enc_tail_forward(const float* cnn_out, int64_t frame_stride, int frames, int H, int W, int C, void* tiles,
+                         size_t tiles_bytes, const void* workspace, size_t workspace_bytes, int max_ctas, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Hot path 2: autoregressive slot-Transformer rollout                        */

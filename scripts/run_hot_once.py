@@ -20,7 +20,9 @@ if os.environ.get('SA_NO_TC'):
 with torch.no_grad():
     for _ in range(int(os.environ.get('REPS', '3'))):
         s = sa(feats, init)
-        ro(s.view(64, 6, 6, 128), 10)
-    x = torch.randn((640, 6, 4, 128, 128), device=dev)
-    engine.decode_combine(x, want_seg=True)
+        if not os.environ.get('SA_ONLY'):
+            ro(s.view(64, 6, 6, 128), 10)
+    if not os.environ.get('SA_ONLY'):
+        x = torch.randn((640, 6, 4, 128, 128), device=dev)
+        engine.decode_combine(x, want_seg=True)
 torch.cuda.synchronize()

@@ -15,6 +15,7 @@ from torch.nn import functional as F
 from ...compat.nerv.models import conv_norm_act, deconv_norm_act, deconv_out_shape
 from ...compat.nerv.training import BaseModel
 from .predictor import ResidualMLPPredictor, RNNPredictorWrapper, TransformerPredictor
+from ...engine import ENC_TAIL_KEYS, SFB_SA_NO_TCGEN05, EncoderTailEngine, FeatureTiles
 from .slot_attention import SlotAttention
 from .utils import SoftPositionEmbed, assert_shape, torch_cat
 
@@ -184,6 +185,28 @@ class StoSAVi(BaseModel):
         x = self.encoder_pos_embedding(x).flatten(2, 3).permute(0, 2, 1).contiguous()
         return self.encoder_out_layer(x)
 
+    # -- encoder tail fused into the Slot Attention input format ------------------------------
+    # In inference the MLP after the CNN (+ positional embedding, both LayerNorms) runs as ONE sm_100a kernel that
+    # writes the fp16 operand tiles Slot Attention streams (csrc/enc_tail.cu): the fp32 [B*T, 4096, C] feature grid
+    # of the reference is never formed.  Shapes outside the kernel's envelope keep the stock layers.
+    fuse_encoder_tail = True
+
+    def _encoder_tail_fusable(self, img):
+        sa = self.slot_attention
+        return (self.fuse_encoder_tail and img.is_cuda and not self.training and not torch.is_grad_enabled()
+                and self.enc_out_channels == 128 and self.visual_channels == 64 and self.dtype == torch.float32
+                and sa.in_features == 128 and sa.slot_size == 128 and sa.num_slots <= 8
+                and not (sa.engine_flags & SFB_SA_NO_TCGEN05))
+
+    def _get_encoder_tiles(self, img):
+        """img [N, 3, H, W] -> FeatureTiles [N] (same role as _get_encoder_out, savi.py:367-377)."""
+        if '_enc_tail_engine' not in self.__dict__:
+            self.__dict__['_enc_tail_engine'] = EncoderTailEngine()
+        named = dict(self.named_parameters())
+        x = self.encoder(img).type(self.dtype)
+        return self._enc_tail_engine.forward(x, {k: named[k].detach() for k in ENC_TAIL_KEYS}, self.enc_out_channels,
+                                             max_ctas=self.slot_attention.max_ctas)
+
     def _frame_loop(self, feats, prev_slots):
         """The serial per-frame chain (reference savi.py:393-410): predictor -> kernel_dist_layer -> sample ->
         Slot Attention, T times.  feats [B, T, N, C] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D])."""
@@ -224,15 +247,18 @@ class StoSAVi(BaseModel):
         if hasattr(pred, 'rnn'):
             pred.rnn.flatten_parameters()                   # before the key: flattening re-points the weights once
         key = self._graph_key(feats, prev_slots, h_in is not None)
+        tiled = isinstance(feats, FeatureTiles)
+        raw = feats.data if tiled else feats
         cache = self.__dict__.setdefault('_loop_graphs', {})
         ent = cache.get(key)
         if ent is None:
             if len(cache) >= 4:
                 cache.clear()                               # weights changed or many shapes: start over
-            s_feats = torch.empty_like(feats)
+            s_raw = torch.empty_like(raw)
+            s_feats = FeatureTiles(s_raw, feats.N, feats.C) if tiled else s_raw
             s_prev = torch.empty_like(prev_slots) if prev_slots is not None else None
             s_h = tuple(torch.empty_like(h) for h in h_in) if h_in is not None else None
-            s_feats.copy_(feats)
+            s_raw.copy_(raw)
             if s_prev is not None:
                 s_prev.copy_(prev_slots)
             if s_h is not None:
@@ -255,11 +281,11 @@ class StoSAVi(BaseModel):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out, h_out = run()
-            ent = cache[key] = (graph, s_feats, s_prev, s_h, out, h_out, (pred.step - step0) if stateful else 0)
+            ent = cache[key] = (graph, s_raw, s_prev, s_h, out, h_out, (pred.step - step0) if stateful else 0)
             if stateful:
                 pred.step = step0
-        graph, s_feats, s_prev, s_h, out, h_out, nsteps = ent
-        s_feats.copy_(feats)
+        graph, s_raw, s_prev, s_h, out, h_out, nsteps = ent
+        s_raw.copy_(raw)
         if s_prev is not None:
             s_prev.copy_(prev_slots)
         if s_h is not None:
@@ -278,7 +304,10 @@ class StoSAVi(BaseModel):
     def encode(self, img, prev_slots=None):
         """img [B, T, 3, H, W] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D], features)."""
         B, T = img.shape[:2]
-        feats = self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
+        if self._encoder_tail_fusable(img):
+            feats = self._get_encoder_tiles(img.flatten(0, 1)).unflatten(0, (B, T))
+        else:
+            feats = self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
         if self.use_cuda_graph and feats.is_cuda and not torch.is_grad_enabled() and not self.training:
             try:
                 dists, slots = self._frame_loop_graphed(feats.contiguous(), prev_slots)

@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsfb200.so')
 LIB_DEBUG = os.path.join(LIBDIR, 'libsfb200_debug.so')
-SOURCES = ["capi.cu", "sa_pass.cu", "sa_pass_tc.cu", "sa_update.cu", "ro_kernel.cu", "ro_umma.cu", "ro_pack.cu", "decode_combine.cu",
+SOURCES = ["capi.cu", "sa_pass.cu", "sa_pass_tc.cu", "enc_tail.cu", "sa_update.cu", "ro_kernel.cu", "ro_umma.cu", "ro_pack.cu", "decode_combine.cu",
            "sa_pass_split.cu"]
 DEBUG_SOURCES = ["umma_test.cu"]
 HEADERS = ['common.cuh', 'sa_kernel.h', 'ro_kernel.h', 'ro_attn.cuh', 'umma.cuh', 'decode_kernel.h', os.path.join('..', '..', 'include', 'sfb200.h')]

@@ -149,12 +149,17 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     for (size_t i = 0; i < sizeof(sfb_sa_weights) / sizeof(const float*); ++i)
         if (!wp[i]) return SFB_E_NULL;
     if (B < 0 || N < 1 || K < 1 || K > 8 || n_iter < 1 || max_ctas < 0) return SFB_E_BAD_SHAPE;
-    if (feat_dtype != SFB_DTYPE_F32 && feat_dtype != SFB_DTYPE_BF16) return SFB_E_BAD_SHAPE;
+    if (feat_dtype != SFB_DTYPE_F32 && feat_dtype != SFB_DTYPE_BF16 && feat_dtype != SFB_DTYPE_TILES16) return SFB_E_BAD_SHAPE;
     if (!sfb::sa_shape_supported(C, D, Dm)) return SFB_E_BAD_SHAPE;
-    if (feat_batch_stride < (int64_t)N * C || (feat_batch_stride & 7)) return SFB_E_BAD_ALIGN;
+    const bool tiles_in = feat_dtype == SFB_DTYPE_TILES16;
+    if (tiles_in && (C != 128 || (flags & SFB_SA_NO_TCGEN05))) return SFB_E_BAD_SHAPE;   // tiles feed the tcgen05 passes only
+    if (tiles_in ? (feat_batch_stride < (int64_t)sfb_enc_tail_tiles_bytes(1, N, C) / 2)
+                 : (feat_batch_stride < (int64_t)N * C)) return SFB_E_BAD_SHAPE;
+    if (feat_batch_stride & 7) return SFB_E_BAD_ALIGN;
     if (!aligned16(feats) || !aligned16(slots_in) || !aligned16(slots_out) || !aligned16(workspace))
         return SFB_E_BAD_ALIGN;
-    if (workspace_bytes < sfb_sa_workspace_bytes(B, N, C, D, Dm, n_iter, chunk_frames)) return SFB_E_WORKSPACE;
+    // (given tiles are read in place: no x^ ring of its own, as with a single iteration)
+    if (workspace_bytes < sfb_sa_workspace_bytes(B, N, C, D, Dm, tiles_in ? 1 : n_iter, chunk_frames)) return SFB_E_WORKSPACE;
     DevInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
@@ -165,7 +170,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     if (max_ctas > 0 && max_ctas < di.sms) { di.sms = max_ctas; cta_limited = true; }
     const int chunk = sa_pick_chunk(B, N, C, n_iter, chunk_frames);
     sfb::SAWorkspace ws;
-    sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, n_iter, &ws);
+    sfb::sa_workspace_layout(B, chunk, N, C, D, Dm, tiles_in ? 1 : n_iter, &ws);
     char* base = reinterpret_cast<char*>(workspace);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
@@ -194,6 +199,8 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     pp.ln_w = w->norm_inputs_weight; pp.ln_b = w->norm_inputs_bias;
     pp.B = B; pp.N = N; pp.K = K; pp.nchunk = ws.nchunk; pp.chunk_px = ws.chunk_px;
     pp.pstride = ws.pstride; pp.n16 = ws.n16; pp.xhat_frames = ws.xhat_frames > 0 ? ws.xhat_frames : 1;
+    pp.xhat_fstride = (long long)ws.n16 * C * 2;
+    if (tiles_in) { pp.xhat_frames = B; pp.xhat_fstride = (long long)feat_batch_stride * 2; }
     pp.prof = g_prof; pp.prof_cap = g_prof_cap;
     pp.cta_limited = cta_limited ? 1 : 0;
     pp.split = (flags & SFB_SA_SPLIT_ON) ? 1 : ((flags & SFB_SA_SPLIT_OFF) ? 0 : -1);
@@ -201,6 +208,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     // tcgen05 passes (C = 128) unless the caller asks for the mma.sync ones; q~ then lives in the operand layout
     const bool use_tc = !(flags & SFB_SA_NO_TCGEN05) && sfb::sa_pass_tc_supported(pp, C);
     up.qt_swz = use_tc ? 1 : 0;
+    if (tiles_in && !use_tc) return SFB_E_BAD_SHAPE;
 
     for (int f0 = 0; f0 < B; f0 += chunk) {
         const int nf = (B - f0) < chunk ? (B - f0) : chunk;
@@ -212,9 +220,11 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
         g_launches.fetch_add(1);
         for (int it = 0; it < n_iter; ++it) {
             const bool last = (it == n_iter - 1);
-            pp.xhat = (n_iter > 1) ? reinterpret_cast<__half*>(base + ws.xhat) : nullptr;
+            pp.xhat = tiles_in ? reinterpret_cast<__half*>(const_cast<void*>(feats))
+                               : ((n_iter > 1) ? reinterpret_cast<__half*>(base + ws.xhat) : nullptr);
             pp.seg_mask = last ? seg_mask : nullptr;
-            e = use_tc ? sfb::sa_pass_tc_launch(pp, it == 0, di.sms, st)
+            pp.write_xsum = (tiles_in && it == 0) ? 1 : 0;
+            e = use_tc ? sfb::sa_pass_tc_launch(pp, it == 0 && !tiles_in, di.sms, st)
                        : sfb::sa_pass_launch(pp, C, it == 0, di.sms, di.smem_optin, st);
             if (e != cudaSuccess) return cuda_err(e);
             g_launches.fetch_add(1);
@@ -224,6 +234,64 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
             g_launches.fetch_add(1);
         }
     }
+    return SFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Encoder tail (section 8 f1)
+// ------------------------------------------------------------------------------------------
+size_t sfb_enc_tail_workspace_bytes(int C) { return C == 128 ? sfb::enc_tail_workspace_bytes() : 0; }
+
+size_t sfb_enc_tail_tiles_bytes(int frames, int N, int C) {
+    if (frames < 0 || N < 1 || C != 128) return 0;
+    // the tile count of a frame is the one sfb_sa_forward's items cover (sa_workspace_layout: n16 / 128)
+    sfb::SAWorkspace ws;
+    sfb::sa_workspace_layout(1, 1, N, C, C, 2 * C, 1, &ws);
+    return (size_t)frames * ws.n16 * C * 2;
+}
+
+int sfb_enc_tail_prepare(const sfb_enc_tail_weights* w, int C, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!w || !workspace) return SFB_E_NULL;
+    const float* const* wp = reinterpret_cast<const float* const*>(w);
+    for (size_t i = 0; i < sizeof(sfb_enc_tail_weights) / sizeof(const float*); ++i)
+        if (!wp[i]) return SFB_E_NULL;
+    if (C != 128) return SFB_E_BAD_SHAPE;
+    if (!aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    if (workspace_bytes < sfb::enc_tail_workspace_bytes()) return SFB_E_WORKSPACE;
+    cudaError_t e = sfb::enc_tail_prep_launch(
+        w->encoder_pos_embedding_dense_weight, w->encoder_pos_embedding_dense_bias, w->encoder_out_layer_0_weight,
+        w->encoder_out_layer_0_bias, w->encoder_out_layer_1_weight, w->encoder_out_layer_1_bias,
+        w->encoder_out_layer_3_weight, w->encoder_out_layer_3_bias, reinterpret_cast<char*>(workspace),
+        reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
+    return SFB_OK;
+}
+
+int sfb_enc_tail_forward(const float* cnn_out, int64_t frame_stride, int frames, int H, int W, int C, void* tiles,
+                         size_t tiles_bytes, const void* workspace, size_t workspace_bytes, int max_ctas, void* stream) {
+    if (frames == 0) return SFB_OK;
+    if (!cnn_out || !tiles || !workspace) return SFB_E_NULL;
+    if (frames < 0 || H < 1 || W < 1 || C != 128 || max_ctas < 0) return SFB_E_BAD_SHAPE;
+    const long long N = (long long)H * W;
+    if (N > (1 << 24) || (N & 3)) return SFB_E_BAD_SHAPE;                  // TMA row pitch: multiples of 16 bytes
+    if (frame_stride < 64 * N || (frame_stride & 3)) return SFB_E_BAD_ALIGN;
+    if (!aligned16(cnn_out) || !aligned16(tiles) || !aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    if (workspace_bytes < sfb::enc_tail_workspace_bytes()) return SFB_E_WORKSPACE;
+    if (tiles_bytes < sfb_enc_tail_tiles_bytes(frames, (int)N, C)) return SFB_E_WORKSPACE;
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
+    if (max_ctas > 0 && max_ctas < di.sms) di.sms = max_ctas;
+    // the kernel tiles a frame in 128-pixel tiles up to ceil(N / 128); the tile buffer of a frame holds n16 / 128
+    // tiles (a multiple of the pass kernel's chunk): tiles beyond ceil(N / 128) are never read with pixels < N
+    sfb::SAWorkspace ws;
+    sfb::sa_workspace_layout(1, 1, (int)N, C, C, 2 * C, 1, &ws);
+    cudaError_t e = sfb::enc_tail_launch(cnn_out, frame_stride, frames, H, W, tiles, reinterpret_cast<const char*>(workspace),
+                                         di.sms, ws.n16 / 128, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
     return SFB_OK;
 }
 

@@ -39,6 +39,8 @@ struct SAPassParams {
     int feat_esize;
     long long feat_bstride;    // elements between frames
     __half* xhat;              // nullable when there is no later pass
+    long long xhat_fstride;    // bytes between frames of the x^ ring / tile buffer (tcgen05 passes)
+    int write_xsum;            // tcgen05 ring pass: also write sum_n t[n] (the first iteration runs on given tiles)
     const __half* qt;          // per frame: hi [8][C], lo [8][C], 8 fp32 logit biases
     float* partials;
     float* seg_mask;           // nullable; written only by the last pass
@@ -81,6 +83,13 @@ cudaError_t sa_pass_split_launch(const SAPassParams& p, int sms, cudaStream_t st
 bool sa_pass_tc_supported(const SAPassParams& p, int C);
 cudaError_t sa_pass_tc_launch(const SAPassParams& p, bool first, int sms, cudaStream_t st);
 cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st);
+// encoder tail (enc_tail.cu)
+size_t enc_tail_workspace_bytes();
+cudaError_t enc_tail_prep_launch(const float* pos_w, const float* pos_b, const float* ln_w, const float* ln_b,
+                                 const float* w1, const float* b1, const float* w2, const float* b2, char* ws,
+                                 cudaStream_t st);
+cudaError_t enc_tail_launch(const float* cnn, long long frame_stride, int frames, int H, int W, void* tiles,
+                            const char* ws, int sms, int tiles_frame, cudaStream_t st);
 bool sa_shape_supported(int C, int D, int DM);
 
 }  // namespace sfb

@@ -406,7 +406,6 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
         for (int j = 0; j < 8; ++j) xo[j] = (uint32_t)((j ^ (lane & 7)) << 4);
         const bool store_xhat = p.xhat != nullptr;
         const uint64_t pol_x = l2_policy_evict_last();
-        const int tiles_frame = p.n16 / TC_TILE_PX;
         int s = lw;                           // stage of sub-tile n (NST == LN warps: always lw)
         uint32_t spar = 0;
         for (int n = lw; n < total_sub; n += 8) {
@@ -476,8 +475,8 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
             __syncwarp();
             if (lane == 0) {
                 if (store_xhat) {
-                    unsigned char* dst = reinterpret_cast<unsigned char*>(p.xhat) +
-                        ((size_t)(f % p.xhat_frames) * tiles_frame + tile_in_frame) * TC_TILE_BYTES + sub * 4096;
+                    unsigned char* dst = reinterpret_cast<unsigned char*>(p.xhat) + (size_t)(f % p.xhat_frames) * p.xhat_fstride +
+                                         (size_t)tile_in_frame * TC_TILE_BYTES + sub * 4096;
                     const unsigned char* src = tiles + (size_t)b * TC_TILE_BYTES + sub * 4096;
                     bulk_s2g(dst, src, 4096, pol_x);
                     bulk_s2g(dst + TC_PANEL_BYTES, src + TC_PANEL_BYTES, 4096, pol_x);
@@ -557,13 +556,12 @@ __global__ void __launch_bounds__(256, 1) sa_pass_tc_next_kernel(const SAPassPar
     const ItemIter it(p);
 
     if (warp < Cfg::SM_WARPS) {
-        tc_softmax_role(p, pbuf, csw, bars, tmem, warp, lane, false);
+        tc_softmax_role(p, pbuf, csw, bars, tmem, warp, lane, p.write_xsum != 0);
     } else if (warp == Cfg::WARP_PROD) {
         if (lane == 0) {
             const bool ring_fits_l2 = (size_t)p.xhat_frames * p.n16 * TC_C * 2 <= ((size_t)48 << 20);
             const uint64_t pol = ring_fits_l2 ? l2_policy_evict_last() : l2_policy_evict_first();
             const uint64_t pol_q = l2_policy_evict_last();
-            const int tiles_frame = p.n16 / TC_TILE_PX;
             int tb = 0;
             uint32_t tbpar = 0;
             for (int il = 0; il < it.my_items; ++il) {
@@ -579,8 +577,8 @@ __global__ void __launch_bounds__(256, 1) sa_pass_tc_next_kernel(const SAPassPar
                     mbar_wait(&bars[TB_TFREE + tb], tbpar ^ 1u);
                     mbar_arrive_expect_tx(&bars[TB_TREADY + tb], TC_TILE_BYTES);
                     bulk_g2s(tiles + (size_t)tb * TC_TILE_BYTES,
-                             reinterpret_cast<const unsigned char*>(p.xhat) +
-                                 ((size_t)(f % p.xhat_frames) * tiles_frame + tile_in_frame) * TC_TILE_BYTES,
+                             reinterpret_cast<const unsigned char*>(p.xhat) + (size_t)(f % p.xhat_frames) * p.xhat_fstride +
+                                 (size_t)tile_in_frame * TC_TILE_BYTES,
                              TC_TILE_BYTES, &bars[TB_TREADY + tb], pol);
                     if (++tb == Cfg::NTB) { tb = 0; tbpar ^= 1u; }
                 }

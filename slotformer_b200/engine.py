@@ -23,6 +23,7 @@ SFB_RO_MMA_SYNC = 1
 
 SFB_DTYPE_F32 = 0
 SFB_DTYPE_BF16 = 1
+SFB_DTYPE_TILES16 = 2
 SFB_RO_SLIDE = 0
 SFB_RO_GROW = 1
 RO_MAX_LAYERS = 16
@@ -32,6 +33,11 @@ SA_WEIGHT_KEYS = (
     'project_q.1.weight', 'project_k.weight', 'project_v.weight', 'gru.weight_ih',
     'gru.weight_hh', 'gru.bias_ih', 'gru.bias_hh', 'mlp.0.weight', 'mlp.0.bias',
     'mlp.1.weight', 'mlp.1.bias', 'mlp.3.weight', 'mlp.3.bias')
+
+ENC_TAIL_KEYS = (
+    'encoder_pos_embedding.dense.weight', 'encoder_pos_embedding.dense.bias',
+    'encoder_out_layer.0.weight', 'encoder_out_layer.0.bias', 'encoder_out_layer.1.weight',
+    'encoder_out_layer.1.bias', 'encoder_out_layer.3.weight', 'encoder_out_layer.3.bias')
 
 RO_LAYER_KEYS = (
     'self_attn.in_proj_weight', 'self_attn.in_proj_bias', 'self_attn.out_proj.weight',
@@ -45,6 +51,10 @@ class SfbError(RuntimeError):
 
 class _SAWeights(ctypes.Structure):
     _fields_ = [(k.replace('.', '_'), ctypes.c_void_p) for k in SA_WEIGHT_KEYS]
+
+
+class _EncTailWeights(ctypes.Structure):
+    _fields_ = [(k.replace('.', '_'), ctypes.c_void_p) for k in ENC_TAIL_KEYS]
 
 
 class _ROLayer(ctypes.Structure):
@@ -85,6 +95,15 @@ def _bind(path, debug):
         c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p,
         c.POINTER(_SAWeights), c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
         c.c_float, c.c_int, c.c_int, c.c_uint, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.sfb_enc_tail_workspace_bytes.restype = c.c_size_t
+    lib.sfb_enc_tail_workspace_bytes.argtypes = [c.c_int]
+    lib.sfb_enc_tail_tiles_bytes.restype = c.c_size_t
+    lib.sfb_enc_tail_tiles_bytes.argtypes = [c.c_int, c.c_int, c.c_int]
+    lib.sfb_enc_tail_prepare.restype = c.c_int
+    lib.sfb_enc_tail_prepare.argtypes = [c.POINTER(_EncTailWeights), c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.sfb_enc_tail_forward.restype = c.c_int
+    lib.sfb_enc_tail_forward.argtypes = [c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p,
+                                         c.c_size_t, c.c_void_p, c.c_size_t, c.c_int, c.c_void_p]
     lib.sfb_rollout_workspace_bytes.restype = c.c_size_t
     lib.sfb_rollout_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int]
     lib.sfb_rollout_prepare.restype = c.c_int
@@ -136,7 +155,8 @@ def use_debug_library():
 def exported_symbols(debug=False):
     """Names declared in include/sfb200.h (used by the CPU-side ABI test)."""
     names = ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
-             'sfb_sa_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
+             'sfb_sa_forward', 'sfb_enc_tail_workspace_bytes', 'sfb_enc_tail_tiles_bytes', 'sfb_enc_tail_prepare',
+             'sfb_enc_tail_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
              'sfb_rollout_forward', 'sfb_decode_combine', 'sfb_postproc_mask']
     if debug:
         names += ['sfb_debug_set_profile', 'sfb_debug_umma_gemm']
@@ -270,6 +290,101 @@ def _weights_key(tensors):
 
 
 # --------------------------------------------------------------------------- #
+# Encoder tail
+# --------------------------------------------------------------------------- #
+class FeatureTiles:
+    """LayerNorm-ed per-pixel features as the fp16 operand tiles of the tcgen05 Slot Attention passes
+    (sfb_enc_tail_forward output, SFB_DTYPE_TILES16): stands in for the reference's fp32 [..., N, C] feature grid
+    wherever it is only indexed over its leading (frame) dimensions and handed to ``SlotAttention``.
+    ``data``: fp16 [*lead, halves_per_frame]; one frame = ceil-to-chunk(N) / 128 tiles of 32 KB."""
+
+    def __init__(self, data, N, C):
+        self.data, self.N, self.C = data, int(N), int(C)
+
+    shape = property(lambda self: tuple(self.data.shape[:-1]) + (self.N, self.C))
+    device = property(lambda self: self.data.device)
+    is_cuda = property(lambda self: self.data.is_cuda)
+    dtype = torch.float16
+    requires_grad = False
+
+    def dim(self):
+        return self.data.dim() + 1
+
+    def __getitem__(self, idx):
+        return FeatureTiles(self.data[idx], self.N, self.C)
+
+    def unflatten(self, dim, sizes):
+        assert dim == 0
+        return FeatureTiles(self.data.unflatten(0, sizes), self.N, self.C)
+
+    def detach(self):
+        return self
+
+    def contiguous(self):
+        return FeatureTiles(self.data.contiguous(), self.N, self.C)
+
+    def to_dense(self):
+        """[*lead, N, C] fp32 values of t (for tests): undoes the tile / panel / 128-byte-swizzle layout."""
+        lead = self.data.shape[:-1]
+        d = self.data.reshape(-1, self.data.shape[-1] // 16384, 2, 128, 8, 8)     # frame, tile, panel, row, chunk, 8 halves
+        rows = torch.arange(128, device=d.device)
+        chunk = torch.arange(8, device=d.device)[None, :] ^ (rows[:, None] & 7)         # logical chunk -> stored chunk
+        d = torch.gather(d, 4, chunk[None, None, None, :, :, None].expand(d.shape[0], d.shape[1], 2, 128, 8, 8))
+        d = d.permute(0, 1, 3, 2, 4, 5).reshape(d.shape[0], -1, 128)                # frame, pixel, channel
+        return d[:, :self.N].float().reshape(*lead, self.N, self.C)
+
+
+class EncoderTailEngine:
+    """Launcher state for sfb_enc_tail_prepare / sfb_enc_tail_forward."""
+
+    def __init__(self):
+        self._ws = None
+        self._key = None
+        self._captured = []
+
+    def invalidate(self):
+        self._key = None
+
+    def forward(self, cnn_out, weights, C, max_ctas=0):
+        """cnn_out [F, 64, H, W] f32 (CNN encoder output, NCHW) -> FeatureTiles [F] (N = H*W, C features)."""
+        lib = load()
+        _require_cuda_f32('cnn_out', cnn_out)
+        if cnn_out.dim() != 4 or cnn_out.shape[1] != 64:
+            raise SfbError(f'cnn_out must be [frames, 64, H, W], got {tuple(cnn_out.shape)}')
+        cnn_out = cnn_out.contiguous()
+        F_, _, H, W = cnn_out.shape
+        dev = cnn_out.device
+        per_frame = int(lib.sfb_enc_tail_tiles_bytes(1, H * W, C))
+        ws_bytes = int(lib.sfb_enc_tail_workspace_bytes(C))
+        if per_frame == 0 or ws_bytes == 0:
+            raise SfbError(f'unsupported encoder-tail shape C={C} H={H} W={W}')
+        tiles = torch.empty((F_, per_frame // 2), dtype=torch.float16, device=dev)
+        if F_ == 0:
+            return FeatureTiles(tiles, H * W, C)
+        cw = _EncTailWeights()
+        wt = []
+        for k in ENC_TAIL_KEYS:
+            t = weights[k]
+            _require_cuda_f32(k, t)
+            t = t if t.is_contiguous() else t.contiguous()
+            wt.append(t)
+            setattr(cw, k.replace('.', '_'), t.data_ptr())
+        with torch.cuda.device(dev):
+            if self._ws is None or self._ws.device != dev:
+                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                self._key = None
+            if torch.cuda.is_current_stream_capturing() and not any(w is self._ws for w in self._captured):
+                self._captured.append(self._ws)
+            key = _weights_key(wt)
+            if key != self._key:
+                _check(lib.sfb_enc_tail_prepare(ctypes.byref(cw), C, self._ws.data_ptr(), ws_bytes, _stream(dev)))
+                self._key = key
+            _check(lib.sfb_enc_tail_forward(cnn_out.data_ptr(), cnn_out.stride(0), F_, H, W, C, tiles.data_ptr(),
+                                            tiles.numel() * 2, self._ws.data_ptr(), ws_bytes, int(max_ctas), _stream(dev)))
+        return FeatureTiles(tiles, H * W, C)
+
+
+# --------------------------------------------------------------------------- #
 # Slot Attention
 # --------------------------------------------------------------------------- #
 class SlotAttentionEngine:
@@ -293,7 +408,12 @@ class SlotAttentionEngine:
         Returns slots [B,K,D] (and seg mask [B,K,N] if ``return_mask``).
         """
         lib = load()
-        if isinstance(feats, torch.Tensor) and feats.dtype == torch.bfloat16 and feats.is_cuda:
+        tiles = isinstance(feats, FeatureTiles)
+        if tiles:
+            if not feats.is_cuda:
+                raise SfbError('feature tiles must live on a CUDA device')
+            feat_dtype = SFB_DTYPE_TILES16
+        elif isinstance(feats, torch.Tensor) and feats.dtype == torch.bfloat16 and feats.is_cuda:
             feat_dtype = SFB_DTYPE_BF16
         else:
             _require_cuda_f32('inputs', feats)
@@ -303,16 +423,21 @@ class SlotAttentionEngine:
             raise SfbError(f'bad shapes: inputs {tuple(feats.shape)}, slots {tuple(slots.shape)}')
         B, N, C = feats.shape
         K, D = slots.shape[1], slots.shape[2]
-        if feats.stride(2) != 1 or feats.stride(1) != C:
-            feats = feats.contiguous()
-        bstride = feats.stride(0) if B > 1 else N * C
+        if tiles:
+            raw = feats.data if feats.data.stride(-1) == 1 else feats.data.contiguous()
+            bstride = raw.stride(0) if B > 1 else raw.shape[-1]
+            feats = raw
+        else:
+            if feats.stride(2) != 1 or feats.stride(1) != C:
+                feats = feats.contiguous()
+            bstride = feats.stride(0) if B > 1 else N * C
         slots = slots.contiguous()
         dev = feats.device
         if B == 0:
             out = slots.new_zeros((0, K, D))
             return (out, slots.new_zeros((0, K, N))) if return_mask else out
         ws_bytes = int(lib.sfb_sa_workspace_bytes(B, N, C, D, int(mlp_hidden_size),
-                                                  int(num_iterations), int(chunk_frames)))
+                                                  1 if tiles else int(num_iterations), int(chunk_frames)))
         if ws_bytes == 0:
             raise SfbError(f'unsupported Slot Attention shape B={B} N={N} C={C} D={D}')
         if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
