@@ -9,7 +9,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from ...autograd import KernelForward
-from ...engine import SA_WEIGHT_KEYS, SlotAttentionEngine
+from ...engine import SA_WEIGHT_KEYS, FeatureTiles, SlotAttentionEngine
 
 
 class SlotAttention(nn.Module):
@@ -74,8 +74,9 @@ class SlotAttention(nn.Module):
         return (slots, mask) if return_mask else slots
 
     def _kernel(self, inputs, slots, return_mask):
+        # bf16 grids and ready-made operand tiles (FeatureTiles, the fused encoder tail's output) go in as they are
         return self._engine.forward(
-            inputs.detach() if inputs.dtype == torch.bfloat16 else inputs.detach().float(),
+            inputs.detach() if (isinstance(inputs, FeatureTiles) or inputs.dtype == torch.bfloat16) else inputs.detach().float(),
             slots.detach().float(),
             {k: v.detach() for k, v in self._weights().items()},
             self.num_iterations, self.eps, self.mlp_hidden_size, return_mask=return_mask,
@@ -83,8 +84,8 @@ class SlotAttention(nn.Module):
 
     def _run(self, inputs, slots, return_mask):
         assert inputs.dim() == 3 and slots.dim() == 3
-        if not self._needs_autograd(inputs, slots):
-            return self._kernel(inputs, slots, return_mask)
+        if isinstance(inputs, FeatureTiles) or not self._needs_autograd(inputs, slots):
+            return self._kernel(inputs, slots, return_mask)            # (operand tiles carry no gradient: inference only)
         if not inputs.is_cuda:
             return self._autograd_forward(inputs, slots, return_mask)      # CPU autograd (unit tests of the wrappers)
         # gradients required: the FORWARD still runs on the sm_100a kernels; the backward recomputes the operator

@@ -301,7 +301,7 @@ int sfb_enc_tail_forward(const float* cnn_out, int64_t frame_stride, int frames,
 static size_t pad128(int n) { return (size_t)((n + 127) / 128 * 128); }
 // packed fp16 weights; output-feature rows of every matrix are padded to multiples of 128
 static size_t ro_ws_elems(int Ds, int d, int F, int layers) {
-    return pad128(d) * Ds + pad128(Ds) * d +
+    return 2 * (pad128(d) * Ds + pad128(Ds) * d) +        // in_proj / out_proj: hi and lo halves
            (size_t)layers * (pad128(3 * d) * d + pad128(d) * d + pad128(F) * d + pad128(d) * F);
 }
 
@@ -316,7 +316,7 @@ size_t sfb_rollout_workspace_bytes(int Ds, int d, int F, int num_layers) {
     return ro_par_offset(Ds, d, F, num_layers) + (size_t)num_layers * ro_par_floats(d, F) * sizeof(float);
 }
 
-// workspace layout (fp16): w_in [d][Ds] | w_out [Ds][d] | per layer: wqkv [3d][d], wo [d][d], w1 [F][d], w2 [d][F]
+// workspace layout (fp16): w_in [d][Ds] | w_out [Ds][d] | w_in_lo | w_out_lo | per layer: wqkv [3d][d], wo [d][d], w1 [F][d], w2 [d][F]
 int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* workspace,
                         size_t workspace_bytes, void* stream) {
     if (!w || !workspace) return SFB_E_NULL;
@@ -329,10 +329,10 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
     __half* dst = reinterpret_cast<__half*>(workspace);
     struct Job { const float* src; size_t n; };
     cudaError_t e;
-    auto run = [&](const float* src, int N_, int K_) -> int {
+    auto run = [&](const float* src, int N_, int K_, bool lo = false) -> int {
         const size_t n = pad128(N_) * K_;
         if (!src) return SFB_E_NULL;
-        e = sfb::ro_pack2_launch(src, dst, N_, K_, st);
+        e = sfb::ro_pack2_launch(src, dst, N_, K_, st, lo);
         if (e != cudaSuccess) return cuda_err(e);
         g_launches.fetch_add(1);
         dst += n;
@@ -341,6 +341,8 @@ int sfb_rollout_prepare(const sfb_ro_weights* w, int Ds, int d, int F, void* wor
     int rc;
     if ((rc = run(w->in_proj_weight, d, Ds))) return rc;
     if ((rc = run(w->out_proj_weight, Ds, d))) return rc;
+    if ((rc = run(w->in_proj_weight, d, Ds, true))) return rc;
+    if ((rc = run(w->out_proj_weight, Ds, d, true))) return rc;
     for (int l = 0; l < w->num_layers; ++l) {
         const sfb_ro_layer& ly = w->layers[l];
         if ((rc = run(ly.self_attn_in_proj_weight, 3 * d, d))) return rc;
@@ -389,6 +391,8 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
     const __half* ws = reinterpret_cast<const __half*>(workspace);
     p.w_in = ws; ws += pad128(d) * Ds;
     p.w_out = ws; ws += pad128(Ds) * d;
+    p.w_in_lo = ws; ws += pad128(d) * Ds;
+    p.w_out_lo = ws; ws += pad128(Ds) * d;
     p.b_in = w->in_proj_bias; p.b_out = w->out_proj_bias; p.pe = w->enc_pe;
     p.par_g = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + ro_par_offset(Ds, d, F, w->num_layers));
     for (int l = 0; l < w->num_layers; ++l) {

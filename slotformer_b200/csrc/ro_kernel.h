@@ -20,6 +20,7 @@ struct ROParams {
     const __half* w_in;  // packed [d][Ds]
     const float* b_in;
     const __half* w_out; // packed [Ds][d]
+    const __half *w_in_lo, *w_out_lo;   // fp16(w - fp16(w)) of the two, same packing (engine B: three-term products)
     const float* b_out;
     const float* pe;     // [pe_tokens][d]
     const float* par_g;  // [layers][par_floats]: bqkv | bo | b1 | b2 | ln1w | ln1b | ln2w | ln2b (workspace, fp32)
@@ -40,7 +41,7 @@ struct ROParams {
 };
 
 // fp32 [N][Kd] -> fp16 128x64 weight tiles (pairs of swizzled 64x64 panels), rows padded to 128
-cudaError_t ro_pack2_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st);
+cudaError_t ro_pack2_launch(const float* src, __half* dst, int N, int Kd, cudaStream_t st, bool lo = false);
 cudaError_t umma_test_launch(const __half* Wp, const float* X, float* out, int M, int N, int K, cudaStream_t st);
 // chooses hg / fc / buffer layout; returns 0 or -1 if the shape cannot be kept on chip
 // engine A (mma.sync from a TMA-fed panel ring; any supported shape)

@@ -130,6 +130,11 @@ struct BProducer {
     }
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) { emit(op); }
+    // three-term product (W_hi X_hi + W_hi X_lo + W_lo X_hi): the hi tiles pass through the ring twice
+    template <class Pre, class Epi>
+    __device__ __forceinline__ void gemm3(const UOp& hi, const UOp& lo, uint32_t, uint32_t, int, int, Pre, Epi) {
+        emit(hi); emit(hi); emit(lo);
+    }
     template <int HMAX>
     __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int, int, const float*, float, int, unsigned char*, H16Ext) { emit(op); }
     // weight order of the fused FFN: every W1 tile of the chunk, then the W2 k-block pairs in tile order
@@ -201,6 +206,13 @@ struct BMma {
     template <class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, Pre, Epi) {
         issue(op, b_u32, kblock_bytes, ntok, 0u, false, true);      // whole warp, uniform; one elected lane issues
+    }
+    template <class Pre, class Epi>
+    __device__ __forceinline__ void gemm3(const UOp& hi, const UOp& lo, uint32_t bhi_u32, uint32_t blo_u32, int kblock_bytes,
+                                          int ntok, Pre, Epi) {
+        issue(hi, bhi_u32, kblock_bytes, ntok, 0u, false, false);
+        issue(hi, blo_u32, kblock_bytes, ntok, 0u, true, false);
+        issue(lo, bhi_u32, kblock_bytes, ntok, 0u, true, true);     // tile t's accumulator is complete after its third term
     }
     template <int HMAX>
     __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, const float*, float,
@@ -348,6 +360,10 @@ struct BCompute {
         }
         tcgen05_fence_before();
     }
+    template <class Pre, class Epi>
+    __device__ __forceinline__ void gemm3(const UOp& hi, const UOp&, uint32_t, uint32_t, int, int ntok, Pre pre, Epi epi) {
+        gemm(hi, 0u, 0, ntok, pre, epi);
+    }
     template <int HMAX>
     __device__ __forceinline__ void ffn(const FfnArgs& a) {
         const int nt = a.fcw >> 7, dt = a.d >> 7;
@@ -438,15 +454,24 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                                                                : pred + (size_t)(a - p.hist_tokens) * Ds;
                         v = *reinterpret_cast<const float4*>(src + c4);
                     }
-                    uint2 pk; pk.x = pack_h2(v.x, v.y); pk.y = pack_h2(v.z, v.w);
+                    // the slots enter as hi + lo fp16 pairs (lo in the Y buffer, free until the QKV epilogue): in_proj
+                    // and out_proj are three-term products, their operand rounding would otherwise be a third of the
+                    // step's error budget (scripts/ro_error_budget.py)
+                    uint2 pk, pl;
+                    pk.x = pack_h2(v.x, v.y); pk.y = pack_h2(v.z, v.w);
+                    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
+                    const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+                    pl.x = pack_h2(v.x - h0.x, v.y - h0.y); pl.y = pack_h2(v.z - h1.x, v.w - h1.y);
                     *reinterpret_cast<uint2*>(xb + addr_s(r, c4)) = pk;
+                    *reinterpret_cast<uint2*>(yb + addr_s(r, c4)) = pl;
                 }
             }
             R.sync();
             // ---- in_proj + positional encoding -> h ----
             {
                 const UOp op{p.w_in, Ds >> 6, 0, DMODEL >> 7, 0, Ds >> 6};
-                R.gemm(op, x_u32, kbb, Lp,
+                const UOp op_lo{p.w_in_lo, Ds >> 6, 0, DMODEL >> 7, 0, Ds >> 6};
+                R.gemm3(op, op_lo, x_u32, y_u32, kbb, Lp,
                        [&](int f) { return __ldg(p.b_in + f); },
                        [&](int f, int t8, const float (&v)[8], float bi) {
 #pragma unroll
@@ -568,14 +593,18 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
             if (Role::kCompute) {
                 for (int i = tid; i < 16 * DMODEL; i += RO_THREADS) {
                     const int r = i / DMODEL, c = i % DMODEL;
-                    *reinterpret_cast<__half*>(xb + addr_s(r, c)) = __float2half_rn(r < K ? h[(L - K + r) * (DMODEL + RU_HPAD) + c] : 0.f);
+                    const float v = r < K ? h[(L - K + r) * (DMODEL + RU_HPAD) + c] : 0.f;
+                    const __half hi = __float2half_rn(v);
+                    *reinterpret_cast<__half*>(xb + addr_s(r, c)) = hi;
+                    *reinterpret_cast<__half*>(yb + addr_s(r, c)) = __float2half_rn(v - __half2float(hi));
                 }
             }
             R.sync();
             float* dst = pred + (size_t)step * K * Ds;
             {
                 const UOp op{p.w_out, DMODEL >> 6, 0, (Ds + 127) >> 7, 0, DMODEL >> 6};
-                R.gemm(op, x_u32, kbb, 16,
+                const UOp op_lo{p.w_out_lo, DMODEL >> 6, 0, (Ds + 127) >> 7, 0, DMODEL >> 6};
+                R.gemm3(op, op_lo, x_u32, y_u32, kbb, 16,
                        [&](int f) { return f < Ds ? __ldg(p.b_out + f) : 0.f; },
                        [&](int f, int t8, const float (&v)[8], float bi) {
 #pragma unroll

@@ -133,6 +133,29 @@ __device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float dep) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar) + z) : "memory");
 }
 
+// debug timeline (libsfb200_debug.so only): CTA 0, one lane per role stamps (role, tag, tile, clock) records
+#ifdef SFB_DEBUG
+struct TcProf {
+    unsigned long long* buf;
+    int n, cap;
+    __device__ __forceinline__ TcProf(const SAPassParams& p, int role, bool on) {
+        const bool act = on && p.prof != nullptr && blockIdx.x == 0 && p.prof_cap >= 8 * 512;
+        buf = act ? p.prof + role * 512 : nullptr;
+        n = 0; cap = 512;
+    }
+    __device__ __forceinline__ void mark(int tag, int tile) {
+        if (buf != nullptr && n < cap)
+            buf[n++] = ((unsigned long long)tag << 56) | ((unsigned long long)(tile & 0xffff) << 40) |
+                       ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+    }
+};
+#else
+struct TcProf {
+    __device__ __forceinline__ TcProf(const SAPassParams&, int, bool) {}
+    __device__ __forceinline__ void mark(int, int) {}
+};
+#endif
+
 // one lane polls, the warp sleeps at the warp barrier
 __device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity, int lane) {
     if (lane == 0) { while (!mbar_try_wait(bar, parity)) { } }
@@ -186,12 +209,15 @@ __device__ __forceinline__ void tc_mma_role(const SAPassParams& p, unsigned char
     const uint32_t idesc_a = umma_idesc_f16_major(128, 16, true, true);
     const uint32_t tiles_u32 = smem_u32(tiles), q_u32 = smem_u32(qbuf), p_u32 = smem_u32(pbuf);
     const int total = it.my_items * it.tpi;
+    TcProf pf(p, 0, (threadIdx.x & 31) == 0);
 
     // aggregation of tile u (issued one tile behind the logits so that the tensor pipe never waits for softmax)
     auto agg = [&](int u, int ub, uint32_t ubpar) {
         const int iu = u / it.tpi, ju = u - iu * it.tpi;
         if (ju == 0) mbar_wait(&bars[TB_ACCFREE + (iu & 1)], ((iu >> 1) & 1) ^ 1);
+        pf.mark(3, u);
         mbar_wait(&bars[TB_PREADY + (u & 1)], (u >> 1) & 1);
+        pf.mark(4, u);
         tcgen05_fence_after();
         const uint64_t da = umma_desc_mn_sw128(tiles_u32 + (uint32_t)ub * TC_TILE_BYTES, TC_PANEL_BYTES, 1024);
         const uint64_t db = umma_desc_mn_none(p_u32 + (uint32_t)(u & 1) * 2 * TC_PPLANE, 128, TC_PPLANE);
@@ -215,7 +241,9 @@ __device__ __forceinline__ void tc_mma_role(const SAPassParams& p, unsigned char
     for (int il = 0; il < it.my_items; ++il) {
         for (int j = 0; j < it.tpi; ++j, ++t) {
             if (j == 0) mbar_wait(&bars[TB_QREADY + (il & 1)], (il >> 1) & 1);
+            pf.mark(1, t);
             mbar_wait(&bars[TB_TREADY + tb], tbpar);
+            pf.mark(2, t);
             tcgen05_fence_after();
             const uint64_t da = umma_smem_desc(tiles_u32 + (uint32_t)tb * TC_TILE_BYTES);
             const uint64_t db = umma_smem_desc(q_u32 + (uint32_t)(il & 1) * TC_Q_BYTES);
@@ -248,6 +276,7 @@ __device__ __forceinline__ void tc_softmax_role(const SAPassParams& p, unsigned 
     const int K = p.K, N = p.N;
     const int row = 32 * warp + lane;                        // pixel inside the tile / channel at read-out
     const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+    TcProf pf(p, 1, threadIdx.x == 0);
     int t = 0;
     for (int il = 0; il < it.my_items; ++il) {
         int f, chunk;
@@ -264,11 +293,14 @@ __device__ __forceinline__ void tc_softmax_role(const SAPassParams& p, unsigned 
         for (int s = 0; s < 8; ++s) cs[s] = 0.f;
         for (int j = 0; j < it.tpi; ++j, ++t) {
             const int b = t & 1;
+            pf.mark(1, t);
             mbar_wait_lane0(&bars[TB_LOG + b], (t >> 1) & 1, lane);
+            pf.mark(2, t);
             tcgen05_fence_after();
             float lg[16];
             tmem_ld16(lane_base + TC_COL_LOG + 16u * (uint32_t)b, lg);
             tmem_ld_wait();
+            pf.mark(3, t);
             const int px = (chunk * it.tpi + j) * TC_TILE_PX + row;
             float e[8], m = -INFINITY;
 #pragma unroll
@@ -305,10 +337,12 @@ __device__ __forceinline__ void tc_softmax_role(const SAPassParams& p, unsigned 
                 pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
             }
             *reinterpret_cast<uint4*>(pbuf + (size_t)b * 2 * TC_PPLANE + row * 16) = pk;
+            pf.mark(4, t);
             fence_proxy_async();            // P (generic proxy) -> tensor-core reads (async proxy)
             tcgen05_fence_before();         // the logits buffer has been read
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[TB_PREADY + b]);
+            pf.mark(5, t);
         }
         // ---- item end: accumulator read-out (thread = channel) and column sums ----
         float* part = p.partials + ((size_t)f * p.nchunk + chunk) * p.pstride;
@@ -324,7 +358,9 @@ __device__ __forceinline__ void tc_softmax_role(const SAPassParams& p, unsigned 
 #pragma unroll
             for (int s = 0; s < 8; ++s) my_csw[warp * 8 + s] = cs[s];
         }
+        pf.mark(6, t);
         mbar_wait_lane0(&bars[TB_ACC + (il & 1)], (il >> 1) & 1, lane);
+        pf.mark(7, t);
         tcgen05_fence_after();
         float u[16];
         tmem_ld16(lane_base + TC_COL_ACC + 16u * (uint32_t)(il & 1), u);
@@ -408,6 +444,7 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
         const uint64_t pol_x = l2_policy_evict_last();
         int s = lw;                           // stage of sub-tile n (NST == LN warps: always lw)
         uint32_t spar = 0;
+        TcProf pf(p, 2 + (lw >> 2), (lw & 3) == 0 && lane == 0);
         for (int n = lw; n < total_sub; n += 8) {
             const int t = n >> 2, sub = n & 3, b = t & 1;
             const int il = t / it.tpi, j = t - il * it.tpi;
@@ -416,7 +453,9 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
             const int tile_in_frame = chunk * it.tpi + j;
             const int px = tile_in_frame * TC_TILE_PX + sub * TC_SUB_PX + lane;
             const unsigned char* stg = stages + (size_t)s * Cfg::STAGE_BYTES + lane * 128;
+            pf.mark(1, t);
             mbar_wait_lane0(&bars[TB_FULL + s], spar, lane);
+            pf.mark(2, t);
             f32x2 v[TC_C / 2];
             if (EIN == 4) {
 #pragma unroll
@@ -459,8 +498,11 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
             const f32x2 r2 = pack2(rstd, rstd), nb2 = pack2(nb, nb);
             // the tile buffer: free once the aggregation MMAs of tile t-2 have read it and this warp's own
             // x^ stores of tile t-2 (same rows) have read their source
+            pf.mark(3, t);
             mbar_wait_lane0(&bars[TB_TFREE + b], ((t >> 1) & 1) ^ 1, lane);
+            pf.mark(4, t);
             if (store_xhat) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
+            pf.mark(5, t);
             unsigned char* trow = tiles + (size_t)b * TC_TILE_BYTES + (sub * TC_SUB_PX + lane) * 128;
 #pragma unroll
             for (int oc = 0; oc < 16; ++oc) {         // 8 channels -> one 16-byte chunk of the operand row
@@ -471,8 +513,10 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
                 pk.z = pack_h2(lo2(t2), hi2(t2)); pk.w = pack_h2(lo2(t3), hi2(t3));
                 *reinterpret_cast<uint4*>(trow + (oc >> 3) * TC_PANEL_BYTES + xo[oc & 7]) = pk;
             }
+            pf.mark(6, t);
             fence_proxy_async();              // operand rows (generic proxy) -> tensor cores / TMA store
             __syncwarp();
+            pf.mark(7, t);
             if (lane == 0) {
                 if (store_xhat) {
                     unsigned char* dst = reinterpret_cast<unsigned char*>(p.xhat) + (size_t)(f % p.xhat_frames) * p.xhat_fstride +
@@ -484,6 +528,7 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
                 }
                 mbar_arrive(&bars[TB_TREADY + b]);
             }
+            pf.mark(8, t);
         }
         if (store_xhat && lane == 0) bulk_wait_read<0>();
     } else {

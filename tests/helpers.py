@@ -20,6 +20,13 @@ def rel_max(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
+def rel_l2(a, b):
+    """||a-b||_F / ||b||_F -- the relative error of the whole tensor."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
 def sa_module(c, w, device, mask=None):
     from slotformer_b200.base_slots.models import SlotAttention, SlotAttentionWMask
     cls = SlotAttentionWMask if (c['mask'] if mask is None else mask) else SlotAttention

@@ -64,16 +64,16 @@ def test_workspace_sizes(lib):
     assert 0 < one_iter < a < b
     assert a - one_iter >= 8 * 4096 * 128 * 2          # fp16 x^ ring only when n_iter > 1
     assert lib.sfb_sa_workspace_bytes(0, 4096, 128, 128, 256, 2, 0) == 0
-    # fp16 copies of in/out proj + per-layer qkv, out, ffn1, ffn2 (256-byte aligned), then one fp32 block of
+    # fp16 copies of in/out proj (hi and lo halves: three-term products) + per-layer qkv, out, ffn1, ffn2 (256-byte aligned), then one fp32 block of
     # biases + LayerNorm affine per layer (9 d + F floats)
     def up256(n):
         return (n + 255) // 256 * 256
     d, Ds, F, L = 128, 128, 512, 4
-    want = up256((2 * d * Ds + L * (3 * d * d + d * d + 2 * F * d)) * 2) + L * (9 * d + F) * 4
+    want = up256((4 * d * Ds + L * (3 * d * d + d * d + 2 * F * d)) * 2) + L * (9 * d + F) * 4
     assert lib.sfb_rollout_workspace_bytes(Ds, d, F, L) == want
     # output-feature rows are padded to multiples of 128 (out_proj with Ds = 192 -> 256 rows)
     assert lib.sfb_rollout_workspace_bytes(192, 256, 1024, 8) == \
-        up256((256 * 192 + 256 * 256 + 8 * (768 * 256 + 256 * 256 + 2 * 1024 * 256)) * 2) + 8 * (9 * 256 + 1024) * 4
+        up256((2 * (256 * 192 + 256 * 256) + 8 * (768 * 256 + 256 * 256 + 2 * 1024 * 256)) * 2) + 8 * (9 * 256 + 1024) * 4
 
 
 def test_null_and_shape_validation_without_gpu(lib):
