@@ -14,6 +14,7 @@ TAGS = {0: {1: 'wait-tile', 2: 'got-tile(L issue)', 3: 'wait-P', 4: 'got-P(agg i
         1: {1: 'wait-logits', 2: 'got-logits', 3: 'ldtm-done', 4: 'P-stored', 5: 'P-arrived', 6: 'wait-acc', 7: 'got-acc'},
         2: {1: 'wait-stage', 2: 'got-stage', 3: 'wait-tfree', 4: 'got-tfree', 5: 'store-read-done', 6: 'rows-written', 7: 'fenced', 8: 'arrived'}}
 TAGS[3] = TAGS[2]
+TAGS[4] = {3: 'agg wait-P', 4: 'agg got-P (issue)'}
 cap = 8 * 512
 buf = torch.zeros(cap, dtype=torch.int64, device=dev)
 for iters, name in ((1, 'FIRST pass only (no x^ store)'), (2, 'FIRST + NEXT')):
@@ -31,7 +32,7 @@ for iters, name in ((1, 'FIRST pass only (no x^ store)'), (2, 'FIRST + NEXT')):
         lib.sfb_debug_set_profile(None, 0)
     t = buf.cpu().numpy().astype(np.uint64)
     ev = []
-    for role in range(4):
+    for role in range(5):
         seg = t[role * 512:(role + 1) * 512]; seg = seg[seg != 0]
         for v in seg:
             ev.append((int(v & np.uint64(0xFFFFFFFFFF)), role, int(v >> np.uint64(56)), int((v >> np.uint64(40)) & np.uint64(0xffff))))

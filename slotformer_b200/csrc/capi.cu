@@ -224,6 +224,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
                                : ((n_iter > 1) ? reinterpret_cast<__half*>(base + ws.xhat) : nullptr);
             pp.seg_mask = last ? seg_mask : nullptr;
             pp.write_xsum = (tiles_in && it == 0) ? 1 : 0;
+            pp.reverse = it & 1;          // alternate the walk: a pass starts where the previous one ended (L2 reuse)
             e = use_tc ? sfb::sa_pass_tc_launch(pp, it == 0 && !tiles_in, di.sms, st)
                        : sfb::sa_pass_launch(pp, C, it == 0, di.sms, di.smem_optin, st);
             if (e != cudaSuccess) return cuda_err(e);

@@ -62,6 +62,7 @@ enum {
     TB_ACCFREE = 32,       // [2]  ... and has been read out
     TB_QREADY = 34,        // [2]  q~ operand of an item landed
     TB_QFREE = 36,         // [2]  ... and its logits MMAs are done
+    TB_PFREE = 38,         // [2]  the aggregation MMAs have read the P buffer
     TB_WORDS = 40
 };
 
@@ -164,6 +165,10 @@ __device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity, 
 
 template <bool FIRST, int EIN>
 struct TcCfg {
+    // first pass: two operand tile buffers (one per LayerNorm warp group) and one private raw stage per LayerNorm
+    // warp (a warp's consecutive waits on ITS stage are consecutive phases of the barrier; a stage shared between
+    // warps would let a warp wait on a parity that is two phases ahead of the barrier and pass at once);
+    // later passes: five tile buffers fed by TMA directly
     static constexpr int NTB = FIRST ? 2 : 5;                             // operand tile buffers
     static constexpr int NST = FIRST ? 8 : 0;                             // raw 32-pixel stages
     static constexpr int STAGE_BYTES = TC_SUB_PX * TC_C * EIN;            // 16 KB fp32 / 8 KB bf16
@@ -192,55 +197,37 @@ struct ItemIter {
         tpi = p.chunk_px / TC_TILE_PX;
     }
     __device__ __forceinline__ void locate(const SAPassParams& p, int il, int& f, int& chunk) const {
-        const int item = (int)blockIdx.x + il * (int)gridDim.x;
+        const int idx = (int)blockIdx.x + il * (int)gridDim.x;
+        const int item = p.reverse ? items - 1 - idx : idx;
         f = p.frame0 + item / p.nchunk;
         chunk = item % p.nchunk;
     }
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// MMA issuer (whole warp runs the loop uniformly, one elected lane issues)
+// MMA issuers (each warp runs its loop uniformly, one elected lane issues).  Two warps, two instruction streams:
+// the logits of tile t need the operand tile, the aggregation of tile t needs its probabilities.  With one issuer
+// and the order logits(t) -> aggregation(t-1) the release of a tile buffer (commit of the aggregation) queued
+// behind the arrival of the NEXT tile, and the first pass ran at that cycle (4000 clocks per tile, measured with the
+// role timeline); polling both barriers from one warp cost more than it gained (hot spin next to the softmax
+// warps).  Each issuer now blocks on its own barrier.  What the single in-order stream used to guarantee is
+// explicit: the logits issuer waits until the softmax warps have read the logits buffer it overwrites
+// (PREADY of tile t-2), the softmax warps wait until the aggregation that read a P buffer is complete (PFREE).
 // ---------------------------------------------------------------------------------------------------------
 template <int NTB>
-__device__ __forceinline__ void tc_mma_role(const SAPassParams& p, unsigned char* tiles, unsigned char* qbuf,
-                                            unsigned char* pbuf, uint64_t* bars, uint32_t tmem) {
+__device__ __forceinline__ void tc_logits_role(const SAPassParams& p, unsigned char* tiles, unsigned char* qbuf,
+                                               uint64_t* bars, uint32_t tmem) {
     const ItemIter it(p);
     const uint32_t idesc_l = umma_idesc_f16_major(128, 16, false, false);
-    const uint32_t idesc_a = umma_idesc_f16_major(128, 16, true, true);
-    const uint32_t tiles_u32 = smem_u32(tiles), q_u32 = smem_u32(qbuf), p_u32 = smem_u32(pbuf);
-    const int total = it.my_items * it.tpi;
+    const uint32_t tiles_u32 = smem_u32(tiles), q_u32 = smem_u32(qbuf);
     TcProf pf(p, 0, (threadIdx.x & 31) == 0);
-
-    // aggregation of tile u (issued one tile behind the logits so that the tensor pipe never waits for softmax)
-    auto agg = [&](int u, int ub, uint32_t ubpar) {
-        const int iu = u / it.tpi, ju = u - iu * it.tpi;
-        if (ju == 0) mbar_wait(&bars[TB_ACCFREE + (iu & 1)], ((iu >> 1) & 1) ^ 1);
-        pf.mark(3, u);
-        mbar_wait(&bars[TB_PREADY + (u & 1)], (u >> 1) & 1);
-        pf.mark(4, u);
-        tcgen05_fence_after();
-        const uint64_t da = umma_desc_mn_sw128(tiles_u32 + (uint32_t)ub * TC_TILE_BYTES, TC_PANEL_BYTES, 1024);
-        const uint64_t db = umma_desc_mn_none(p_u32 + (uint32_t)(u & 1) * 2 * TC_PPLANE, 128, TC_PPLANE);
-        const uint32_t dcol = tmem + TC_COL_ACC + 16u * (uint32_t)(iu & 1);
-        if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)         // 16 pixels per MMA: 2 KB of tile rows, 256 B of P
-                umma_f16(dcol, da + (uint64_t)((k * 2048) >> 4), db + (uint64_t)((k * 256) >> 4), idesc_a,
-                         (ju | k) != 0);
-            umma_commit(&bars[TB_TFREE + ub]);
-            if (ju == it.tpi - 1) umma_commit(&bars[TB_ACC + (iu & 1)]);
-        }
-        __syncwarp();
-        (void)ubpar;
-    };
-
     int tb = 0;                 // tile buffer of tile t
     uint32_t tbpar = 0;         // its fill parity
-    int pb = 0;                 // tile buffer of tile t - 1
     int t = 0;
     for (int il = 0; il < it.my_items; ++il) {
         for (int j = 0; j < it.tpi; ++j, ++t) {
             if (j == 0) mbar_wait(&bars[TB_QREADY + (il & 1)], (il >> 1) & 1);
+            if (t >= 2) mbar_wait(&bars[TB_PREADY + (t & 1)], ((t - 2) >> 1) & 1);    // logits buffer t & 1 has been read
             pf.mark(1, t);
             mbar_wait(&bars[TB_TREADY + tb], tbpar);
             pf.mark(2, t);
@@ -259,12 +246,43 @@ __device__ __forceinline__ void tc_mma_role(const SAPassParams& p, unsigned char
                 if (j == it.tpi - 1) umma_commit(&bars[TB_QFREE + (il & 1)]);
             }
             __syncwarp();
-            if (t > 0) agg(t - 1, pb, 0);
-            pb = tb;
             if (++tb == NTB) { tb = 0; tbpar ^= 1u; }
         }
     }
-    if (total > 0) agg(total - 1, pb, 0);
+}
+
+template <int NTB>
+__device__ __forceinline__ void tc_agg_role(const SAPassParams& p, unsigned char* tiles, unsigned char* pbuf,
+                                            uint64_t* bars, uint32_t tmem) {
+    const ItemIter it(p);
+    const uint32_t idesc_a = umma_idesc_f16_major(128, 16, true, true);
+    const uint32_t tiles_u32 = smem_u32(tiles), p_u32 = smem_u32(pbuf);
+    TcProf pf(p, 4, (threadIdx.x & 31) == 0);
+    int ub = 0;                 // tile buffer of tile u
+    int u = 0;
+    for (int iu = 0; iu < it.my_items; ++iu) {
+        for (int ju = 0; ju < it.tpi; ++ju, ++u) {
+            if (ju == 0) mbar_wait(&bars[TB_ACCFREE + (iu & 1)], ((iu >> 1) & 1) ^ 1);
+            pf.mark(3, u);
+            mbar_wait(&bars[TB_PREADY + (u & 1)], (u >> 1) & 1);   // P of tile u is in shared memory (and its tile, hence, too)
+            pf.mark(4, u);
+            tcgen05_fence_after();
+            const uint64_t da = umma_desc_mn_sw128(tiles_u32 + (uint32_t)ub * TC_TILE_BYTES, TC_PANEL_BYTES, 1024);
+            const uint64_t db = umma_desc_mn_none(p_u32 + (uint32_t)(u & 1) * 2 * TC_PPLANE, 128, TC_PPLANE);
+            const uint32_t dcol = tmem + TC_COL_ACC + 16u * (uint32_t)(iu & 1);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)         // 16 pixels per MMA: 2 KB of tile rows, 256 B of P
+                    umma_f16(dcol, da + (uint64_t)((k * 2048) >> 4), db + (uint64_t)((k * 256) >> 4), idesc_a,
+                             (ju | k) != 0);
+                umma_commit(&bars[TB_TFREE + ub]);
+                umma_commit(&bars[TB_PFREE + (u & 1)]);
+                if (ju == it.tpi - 1) umma_commit(&bars[TB_ACC + (iu & 1)]);
+            }
+            __syncwarp();
+            if (++ub == NTB) ub = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -336,6 +354,8 @@ __device__ __forceinline__ void tc_softmax_role(const SAPassParams& p, unsigned 
                 pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                 pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
             }
+            // the aggregation of tile t-2 (another issuer's instruction stream) has read this P buffer
+            if (t >= 2) mbar_wait_lane0(&bars[TB_PFREE + b], ((t - 2) >> 1) & 1, lane);
             *reinterpret_cast<uint4*>(pbuf + (size_t)b * 2 * TC_PPLANE + row * 16) = pk;
             pf.mark(4, t);
             fence_proxy_async();            // P (generic proxy) -> tensor-core reads (async proxy)
@@ -395,6 +415,7 @@ __device__ __forceinline__ void tc_init_bars(uint64_t* bars, int ntb, int nst, i
         mbar_init(&bars[TB_ACCFREE + s], 4);
         mbar_init(&bars[TB_QREADY + s], 1);
         mbar_init(&bars[TB_QFREE + s], 1);
+        mbar_init(&bars[TB_PFREE + s], 1);
     }
     fence_mbar_init();
 }
@@ -432,7 +453,7 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
         asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         tc_softmax_role(p, pbuf, csw, bars, tmem, warp, lane, true);
     } else if (warp < Cfg::WARP_PROD) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         // ------------------------------- LayerNorm warps: thread = pixel -------------------------------
         const int lw = warp - Cfg::SM_WARPS;
         const int total_sub = it.my_items * it.tpi * 4;
@@ -442,11 +463,12 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
         for (int j = 0; j < 8; ++j) xo[j] = (uint32_t)((j ^ (lane & 7)) << 4);
         const bool store_xhat = p.xhat != nullptr;
         const uint64_t pol_x = l2_policy_evict_last();
-        int s = lw;                           // stage of sub-tile n (NST == LN warps: always lw)
-        uint32_t spar = 0;
         TcProf pf(p, 2 + (lw >> 2), (lw & 3) == 0 && lane == 0);
         for (int n = lw; n < total_sub; n += 8) {
+            static_assert(Cfg::NST == 8 && Cfg::NTB == 2, "one private stage per LayerNorm warp, one tile buffer per group");
             const int t = n >> 2, sub = n & 3, b = t & 1;
+            const int s = lw;                                       // raw stage of sub-tile n: always this warp's own
+            const uint32_t spar = (uint32_t)(n >> 3) & 1u;
             const int il = t / it.tpi, j = t - il * it.tpi;
             int f, chunk;
             it.locate(p, il, f, chunk);
@@ -489,7 +511,6 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
             // the stage is free once every lane's row is in registers (sm depends on all of them)
             __syncwarp();
             if (lane == 0) mbar_arrive_after(&bars[TB_EMPTY + s], sm);
-            spar ^= 1u;                       // NST == 8 == LN warps: the same stage every round
             const float mu = sm * (1.f / TC_C);
             const float var = fmaxf(fmaf(-mu, mu, sq * (1.f / TC_C)), 0.f);
             const bool valid = px < N;
@@ -532,7 +553,7 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
         }
         if (store_xhat && lane == 0) bulk_wait_read<0>();
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         if (warp == Cfg::WARP_PROD) {
             if (lane == 0) {
                 // ------------------------------- TMA producer -------------------------------
@@ -568,7 +589,9 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
                 }
             }
         } else if (warp == Cfg::WARP_MMA) {
-            tc_mma_role<Cfg::NTB>(p, tiles, qbuf, pbuf, bars, tmem);
+            tc_logits_role<Cfg::NTB>(p, tiles, qbuf, bars, tmem);
+        } else if (warp == Cfg::WARP_MMA + 1) {
+            tc_agg_role<Cfg::NTB>(p, tiles, pbuf, bars, tmem);
         }
     }
     tcgen05_fence_before();
@@ -630,7 +653,9 @@ __global__ void __launch_bounds__(256, 1) sa_pass_tc_next_kernel(const SAPassPar
             }
         }
     } else if (warp == Cfg::WARP_MMA) {
-        tc_mma_role<Cfg::NTB>(p, tiles, qbuf, pbuf, bars, tmem);
+        tc_logits_role<Cfg::NTB>(p, tiles, qbuf, bars, tmem);
+    } else if (warp == Cfg::WARP_MMA + 1) {
+        tc_agg_role<Cfg::NTB>(p, tiles, pbuf, bars, tmem);
     }
     tcgen05_fence_before();
     __syncthreads();

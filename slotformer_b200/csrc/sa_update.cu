@@ -1,7 +1,8 @@
 // Slot Attention: batched slot update (GRU + residual MLP + next q~), weight preparation and
 // workspace layout.  Reference: base_slots/models/savi.py:80 (project_q), :95-100 (GRUCell, MLP).
 //
-// One CTA updates 16*NMB slot rows (2*NMB frames x 8 padded slots).  The fp16 hi/lo weight panels
+// One CTA updates 16*NMB slot rows; rows are packed densely (row R of the launch = frame R / K, slot R % K), so a
+// batch of K = 6 slots costs 6, not 8, rows per frame.  The fp16 hi/lo weight panels
 // (64 x 64, 128B-swizzled, prepared once per call by sa_prep_kernel) are streamed by a producer
 // warp with TMA bulk copies through an mbarrier ring; 8 math warps each own 8 of a panel's 64
 // output columns for all rows.  Every product uses 3-term fp16 splitting
@@ -263,16 +264,18 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
     const SAWeightsDev& w = p.w;
     const int K = p.K, N = p.N;
     const int g = lane >> 2, t4 = lane & 3;
-    const int fl0 = (int)blockIdx.x * (ROWS / 8);            // first local frame of this CTA
-    const int fbase = p.frame0 + fl0;
-    auto row_ok = [&](int r) { return (fl0 + (r >> 3)) < p.nframes && (r & 7) < K; };
+    const int row0 = (int)blockIdx.x * ROWS;                 // first (dense) row of this CTA: row R = frame R / K, slot R % K
+    const int total_rows = p.nframes * K;
+    auto row_ok = [&](int r) { return row0 + r < total_rows; };
+    auto frame_of = [&](int r) { return p.frame0 + (row0 + r) / K; };
+    auto slot_of = [&](int r) { return (row0 + r) % K; };
 
     if (p.do_update) {
         if (Role::kConsumer) {
             // ---- u^ = (sum_chunks U / 1024 + eps*xsum) / (sum_chunks colsum / 1024 + N*eps) ----
             // (all partial-sum loads of a row are issued before the first use: one L2 latency per row)
             for (int r = warp; r < ROWS; r += UPD_WARPS) {
-                const int f = fbase + (r >> 3), slot = r & 7;
+                const int f = frame_of(r), slot = slot_of(r);
                 const bool ok = row_ok(r);
                 float us[C / 32], xs[C / 32], sprev[C / 32], cs = 0.f;
 #pragma unroll
@@ -403,7 +406,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
                         const float sn = sp[row * LDS + col] + acc[mb][e] + ((e & 1) ? b1v : b0);
                         sp[row * LDS + col] = sn;
                         if (row_ok(row))
-                            p.slots_out[((size_t)(fbase + (row >> 3)) * K + (row & 7)) * D + col] = sn;
+                            p.slots_out[((size_t)p.frame0 * K + row0 + row) * D + col] = sn;
                     }
             }
         }
@@ -414,7 +417,7 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
 #pragma unroll
             for (int i = 0; i < D / 32; ++i) {
                 const int c = lane + 32 * i;
-                sp[r * LDS + c] = ok ? __ldg(p.slots_prev + ((size_t)(fbase + (r >> 3)) * K + (r & 7)) * D + c) : 0.f;
+                sp[r * LDS + c] = ok ? __ldg(p.slots_prev + ((size_t)p.frame0 * K + row0 + r) * D + c) : 0.f;
             }
         }
         R.sync();
@@ -435,9 +438,12 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (lane == 0 && fl0 + (r >> 3) < p.nframes) {
-                    float* lb = reinterpret_cast<float*>(p.qt + (size_t)(fbase + (r >> 3)) * p.qt_stride + 2 * 8 * C);
-                    lb[r & 7] = ((r & 7) < K) ? a : 0.f;
+                if (lane == 0 && row_ok(r)) {
+                    float* lb = reinterpret_cast<float*>(p.qt + (size_t)frame_of(r) * p.qt_stride + 2 * 8 * C);
+                    const int slot = slot_of(r);
+                    lb[slot] = a;
+                    if (slot == K - 1)                      // the frame's last slot also clears the padded slots
+                        for (int z = K; z < 8; ++z) lb[z] = 0.f;
                 }
             }
             R.sync();
@@ -454,21 +460,27 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int row = 16 * mb + g + 8 * (e >> 1), col = col0 + (e & 1);
-                        if (fl0 + (row >> 3) < p.nframes) {
-                            const float v = ((row & 7) < K) ? acc[mb][e] : 0.f;
-                            __half* qf = p.qt + (size_t)(fbase + (row >> 3)) * p.qt_stride;
+                        if (row_ok(row)) {
+                            const float v = acc[mb][e];
+                            __half* qf = p.qt + (size_t)frame_of(row) * p.qt_stride;
                             const __half hv = __float2half_rn(v);
                             const __half lv = __float2half_rn(v - __half2float(hv));
-                            if (p.qt_swz) {
-                                // tcgen05 B operand image (sa_pass_tc.cu): rows 0-7 = hi, 8-15 = lo, two 64-channel
-                                // K-major panels of 16 rows x 128 B, 16-byte chunks XOR-swizzled by the row
-                                const int r = row & 7;
-                                const int off = (col >> 6) * 1024 + ((((col & 63) >> 3) ^ r) << 3) + (col & 7);
-                                qf[off + r * 64] = hv;
-                                qf[off + (8 + r) * 64] = lv;
-                            } else {
-                                qf[(row & 7) * C + col] = hv;
-                                qf[8 * C + (row & 7) * C + col] = lv;
+                            const int slot = slot_of(row);
+                            // the frame's last slot also writes the zero rows of the padded slots K .. 7
+                            const int rlast = (slot == K - 1) ? 7 : slot;
+                            for (int r = slot; r <= rlast; ++r) {
+                                const __half hw = (r == slot) ? hv : __float2half_rn(0.f);
+                                const __half lw = (r == slot) ? lv : __float2half_rn(0.f);
+                                if (p.qt_swz) {
+                                    // tcgen05 B operand image (sa_pass_tc.cu): rows 0-7 = hi, 8-15 = lo, two 64-channel
+                                    // K-major panels of 16 rows x 128 B, 16-byte chunks XOR-swizzled by the row
+                                    const int off = (col >> 6) * 1024 + ((((col & 63) >> 3) ^ r) << 3) + (col & 7);
+                                    qf[off + r * 64] = hw;
+                                    qf[off + (8 + r) * 64] = lw;
+                                } else {
+                                    qf[r * C + col] = hw;
+                                    qf[8 * C + r * C + col] = lw;
+                                }
                             }
                         }
                     }
@@ -563,21 +575,22 @@ static cudaError_t update_launch_t(const SAUpdateParams& p, cudaStream_t st) {
     auto kern = sa_update_kernel<C, NMB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    const int frames_per_cta = Cfg::ROWS / 8;
-    const int grid = (p.nframes + frames_per_cta - 1) / frames_per_cta;
+    const int grid = (p.nframes * p.K + Cfg::ROWS - 1) / Cfg::ROWS;      // dense rows: frame R / K, slot R % K
     kern<<<grid, UPD_THREADS + 32, Cfg::SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st) {
-    // 16*NMB rows (2*NMB frames) per CTA.  A CTA's time grows with NMB (41 us at 2, 69 us at 4), every CTA streams
-    // the whole weight set, so: the smallest NMB whose grid still fits one wave of the SMs this call may use.
+    // 16*NMB rows per CTA.  A CTA's time grows with NMB (about 13 us + 14 us per 16 rows), every CTA streams the
+    // whole weight set, so: the smallest NMB whose grid still fits one wave of the SMs this call may use.
+    const int need = (p.nframes * p.K + sms - 1) / sms;           // rows per CTA for a single wave
     if (C == 128) {
-        const int need = (p.nframes + sms - 1) / sms;             // frames per CTA for a single wave
-        if (need <= 4) return update_launch_t<128, 2>(p, st);
-        if (need <= 6) return update_launch_t<128, 3>(p, st);
+        if (need <= 16) return update_launch_t<128, 1>(p, st);
+        if (need <= 32) return update_launch_t<128, 2>(p, st);
+        if (need <= 48) return update_launch_t<128, 3>(p, st);
         return update_launch_t<128, 4>(p, st);
     }
+    if (need <= 16) return update_launch_t<192, 1>(p, st);
     return update_launch_t<192, 2>(p, st);
 }
 
