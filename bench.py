@@ -11,9 +11,12 @@ frames/s = B * (T_in + T_out) / time.  Synthetic inputs, seeded weights (tests/g
 
   value   : inputs already resident in HBM, CUDA-event timed, max over ranks (weak scaling:
             every rank runs its own B=64 clips; the path has no data-path collective).
-  e2e     : same step through the module API with HOST (pinned) inputs: H2D of the feature
-            grids + initial slots and D2H of the extracted + predicted slots inside the timed
-            region.
+  e2e     : same step through the module API with HOST (pinned) inputs, every copy inside the timed
+            region.  The host-side input is the CNN encoder's output (the tensor the reference's
+            _get_encoder_out consumes at savi.py:367, [384, 64, 64, 64] fp32, 403 MB): the fused
+            encoder tail (sfb_enc_tail_forward) turns it into the operand tiles
+            of Slot Attention on the device, so the 806 MB fp32 feature grid never crosses PCIe.
+            e2e.feature_grid_route is the round-1 route (host fp32 feature grid) for continuity.
   roofline: the Slot Attention kernel against the measured HBM peak (algorithmic bytes =
             N*C*4 + 2*K*D*4 per frame).
   cpu_baseline / --impl reference: the UNMODIFIED reference modules (oracle/_ref, collected by
@@ -46,8 +49,8 @@ WORKLOAD = ('OBJ3D SlotFormer rollout, B=64, 128x128 (64x64 feature grid), K=6, 
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the kernels of ONE sfb_sa_forward call on this
 # workload, from the ncu --set full capture summarised in profiles/ (None until captured)
-SA_TRAFFIC_BYTES = 1592e6
-SA_TRAFFIC_SOURCE = 'profiles/r1b_bench_launch_list.txt (ncu dram__bytes_read+write over the 5 SA launches of one step)'
+SA_TRAFFIC_BYTES = 1558e6
+SA_TRAFFIC_SOURCE = 'profiles/r2b_sa_per_kernel_tc_vs_mma.txt (ncu dram__bytes_read+write over the 5 SA launches of one step)'
 
 
 def sa_bytes_per_frame():
@@ -80,6 +83,26 @@ def make_weights():
     sa_w = cases.make_sa_weights(WL['C'], WL['D'], WL['Dm'], seed=13)
     ro_w = cases.make_ro_weights(WL['D'], WL['d'], WL['F'], WL['layers'], seed=22)
     return sa_w, ro_w
+
+
+def make_tail_weights(seed=31):
+    """Encoder tail of StoSAVi (savi.py:126-133, utils.py:52-63): SoftPositionEmbed dense(4 -> 64), LayerNorm(64),
+    Linear(64 -> C), ReLU, Linear(C -> C); seeded like the other synthetic weights."""
+    rs = np.random.RandomState(seed)
+    C = WL['C']
+
+    def lin(o, i):
+        a = np.sqrt(3.0 / i)
+        return rs.uniform(-a, a, size=(o, i)).astype(np.float32)
+
+    return {'encoder_pos_embedding.dense.weight': lin(64, 4),
+            'encoder_pos_embedding.dense.bias': (0.1 * rs.standard_normal(64)).astype(np.float32),
+            'encoder_out_layer.0.weight': (1.0 + 0.1 * rs.standard_normal(64)).astype(np.float32),
+            'encoder_out_layer.0.bias': (0.1 * rs.standard_normal(64)).astype(np.float32),
+            'encoder_out_layer.1.weight': lin(C, 64),
+            'encoder_out_layer.1.bias': (0.1 * rs.standard_normal(C)).astype(np.float32),
+            'encoder_out_layer.3.weight': lin(C, C),
+            'encoder_out_layer.3.bias': (0.1 * rs.standard_normal(C)).astype(np.float32)}
 
 
 # ---- clocks sampler (NVML) --------------------------------------------------------------
@@ -392,80 +415,104 @@ def run_ours(args):
         # extracted + predicted slots back; two steps in flight (double-buffered device staging).
         e2e = None
         if not args.no_e2e:
-            h_feats = torch.empty((frames, N, C), dtype=torch.float32, pin_memory=True)
-            h_feats.copy_(feats)
-            h_init = torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True)
-            h_init.copy_(init)
-            h_slots = [torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-            h_pred = [torch.empty((B, T_out, K, D), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-            d_feats = [torch.empty_like(feats) for _ in range(2)]
-            d_init = [torch.empty_like(init) for _ in range(2)]
-            d_slots = [torch.empty_like(init) for _ in range(2)]
+            tail = engine.EncoderTailEngine()
+            tail_w = {k: torch.from_numpy(v).to(dev) for k, v in make_tail_weights().items()}
             copy_stream = torch.cuda.Stream(dev)
             out_stream = torch.cuda.Stream(dev)
             nchunk = 8
             cf = frames // nchunk
-            done_ev = [None, None]
+            h_init = torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True)
+            h_init.copy_(init)
+            h_slots = [torch.empty((frames, K, D), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            h_pred = [torch.empty((B, T_out, K, D), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            d_init = [torch.empty_like(init) for _ in range(2)]
+            d_slots = [torch.empty_like(init) for _ in range(2)]
 
-            def e2e_submit(i):
-                sl = i & 1
-                if done_ev[sl] is not None:
-                    done_ev[sl].synchronize()            # staging buffers of step i-2 are free again
-                evs = []
-                with torch.cuda.stream(copy_stream):
-                    d_init[sl].copy_(h_init, non_blocking=True)
-                    for c in range(nchunk):
-                        d_feats[sl][c * cf:(c + 1) * cf].copy_(h_feats[c * cf:(c + 1) * cf], non_blocking=True)
-                        e = torch.cuda.Event()
-                        e.record(copy_stream)
-                        evs.append(e)
-                with torch.cuda.stream(pipe.s_sa):
-                    for c in range(nchunk):
-                        pipe.s_sa.wait_event(evs[c])
-                        d_slots[sl][c * cf:(c + 1) * cf] = sa(d_feats[sl][c * cf:(c + 1) * cf],
-                                                              d_init[sl][c * cf:(c + 1) * cf])
-                    ready = torch.cuda.Event()
-                    ready.record(pipe.s_sa)
-                pipe.s_ro.wait_event(ready)
-                with torch.cuda.stream(pipe.s_ro):
-                    pred = ro(d_slots[sl].view(B, T_in, K, D), T_out)
-                    rdone = torch.cuda.Event()
-                    rdone.record(pipe.s_ro)
-                pred.record_stream(out_stream)
-                out_stream.wait_event(rdone)
-                with torch.cuda.stream(out_stream):
-                    h_slots[sl].copy_(d_slots[sl], non_blocking=True)
-                    h_pred[sl].copy_(pred, non_blocking=True)
-                    fin = torch.cuda.Event()
-                    fin.record(out_stream)
-                done_ev[sl] = fin
+            def e2e_route(route):
+                """route 'cnn': host CNN output -> encoder tail -> Slot Attention on operand tiles -> rollout;
+                route 'grid': host fp32 feature grid -> Slot Attention -> rollout (round 1)."""
+                if route == 'cnn':
+                    h_in = torch.empty((frames, 64, 64, 64), dtype=torch.float32, pin_memory=True)
+                    h_in.copy_(torch.randn(h_in.shape, generator=torch.Generator().manual_seed(7 + rank)))
+                else:
+                    h_in = torch.empty((frames, N, C), dtype=torch.float32, pin_memory=True)
+                    h_in.copy_(feats)
+                d_in = [torch.empty(h_in.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+                done_ev = [None, None]
 
-            def e2e_run(n):
-                with pipe:
-                    for i in range(n):
-                        e2e_submit(i)
-                    for e in done_ev:
-                        if e is not None:
-                            e.synchronize()
-                torch.cuda.synchronize(dev)
+                def submit(i):
+                    sl = i & 1
+                    if done_ev[sl] is not None:
+                        done_ev[sl].synchronize()            # staging buffers of step i-2 are free again
+                    evs = []
+                    with torch.cuda.stream(copy_stream):
+                        d_init[sl].copy_(h_init, non_blocking=True)
+                        for c in range(nchunk):
+                            d_in[sl][c * cf:(c + 1) * cf].copy_(h_in[c * cf:(c + 1) * cf], non_blocking=True)
+                            e = torch.cuda.Event()
+                            e.record(copy_stream)
+                            evs.append(e)
+                    with torch.cuda.stream(pipe.s_sa):
+                        for c in range(nchunk):
+                            pipe.s_sa.wait_event(evs[c])
+                            x = d_in[sl][c * cf:(c + 1) * cf]
+                            if route == 'cnn':
+                                x = tail.forward(x, tail_w, C, max_ctas=pipe.sa_ctas)
+                            d_slots[sl][c * cf:(c + 1) * cf] = sa(x, d_init[sl][c * cf:(c + 1) * cf])
+                        ready = torch.cuda.Event()
+                        ready.record(pipe.s_sa)
+                    pipe.s_ro.wait_event(ready)
+                    with torch.cuda.stream(pipe.s_ro):
+                        pred = ro(d_slots[sl].view(B, T_in, K, D), T_out)
+                        rdone = torch.cuda.Event()
+                        rdone.record(pipe.s_ro)
+                    pred.record_stream(out_stream)
+                    out_stream.wait_event(rdone)
+                    with torch.cuda.stream(out_stream):
+                        h_slots[sl].copy_(d_slots[sl], non_blocking=True)
+                        h_pred[sl].copy_(pred, non_blocking=True)
+                        fin = torch.cuda.Event()
+                        fin.record(out_stream)
+                    done_ev[sl] = fin
 
-            e2e_steps = max(3, min(args.steps, 10))
-            e2e_run(2)
-            sync_all()
-            done_ev = [None, None]
-            t0 = time.perf_counter()
-            e2e_run(e2e_steps)
-            dt = (time.perf_counter() - t0) / e2e_steps
-            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            e2e = {'value': world * frames_per_step() / dt, 'unit': UNIT,
-                   'h2d_bytes_per_step': int(h_feats.numel() * 4 + h_init.numel() * 4),
-                   'd2h_bytes_per_step': int(h_slots[0].numel() * 4 + h_pred[0].numel() * 4),
-                   'ms_per_step': dt * 1e3, 'steps': e2e_steps,
-                   'note': f'pinned host buffers, {nchunk}-chunk H2D overlapped with Slot Attention, '
-                           'two steps in flight (PCIe-bound: 806 MB host->device per step)'}
+                def run(n):
+                    with pipe:
+                        for i in range(n):
+                            submit(i)
+                        for e in done_ev:
+                            if e is not None:
+                                e.synchronize()
+                    torch.cuda.synchronize(dev)
+
+                n0 = engine.launch_count()
+                run(2)
+                per_step = (engine.launch_count() - n0) // 2
+                sync_all()
+                done_ev[0] = done_ev[1] = None
+                steps_ = max(3, min(args.steps, 10))
+                t0 = time.perf_counter()
+                run(steps_)
+                dt = (time.perf_counter() - t0) / steps_
+                tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+                assert torch.isfinite(h_pred[0]).all() and torch.isfinite(h_slots[0]).all()
+                res = {'value': world * frames_per_step() / dt, 'unit': UNIT,
+                       'h2d_bytes_per_step': int(h_in.numel() * 4 + h_init.numel() * 4),
+                       'd2h_bytes_per_step': int(h_slots[0].numel() * 4 + h_pred[0].numel() * 4),
+                       'ms_per_step': dt * 1e3, 'steps': steps_, 'gpu_launches_per_step': int(per_step)}
+                del h_in, d_in
+                torch.cuda.empty_cache()
+                return res
+
+            e2e = e2e_route('cnn')
+            e2e['note'] = (f'pinned host buffers; host input = CNN encoder output [{frames}, 64, 64, 64] fp32 (savi.py:367), '
+                           f'{nchunk}-chunk H2D overlapped with encoder tail + Slot Attention on operand tiles, rollout, D2H of '
+                           'slots + predictions; two steps in flight (PCIe-bound)')
+            grid = e2e_route('grid')
+            grid['note'] = 'round-1 route: host fp32 feature grid [384, 4096, 128] (806 MB per step), no encoder tail on the device'
+            e2e['feature_grid_route'] = grid
 
     if rank != 0:
         if world > 1:
@@ -489,7 +536,7 @@ def run_ours(args):
                                'the K timed steps are one CUDA-graph replay (two streams captured)',
                    'serial_ms_per_step': serial_ms, 'serial_sa_ms': serial_sa_ms, 'serial_rollout_ms': serial_ro_ms},
         'clocks': clocks, 'gpu_launches': int(launches),
-        'roofline': {'kernel': 'sfb_sa_forward: sa_prep + sa_update x3 + sa_pass<first> + sa_pass<next>',
+        'roofline': {'kernel': 'sfb_sa_forward: sa_update x3 + sa_pass_tc_first + sa_pass_tc_next (tcgen05 passes)',
                      'bound': 'hbm', 'achieved': sa_gbs, 'peak': pk['hbm'],
                      'unit': 'GB/s', 'frac': sa_gbs / pk['hbm'], 'traffic': SA_TRAFFIC_BYTES,
                      'traffic_source': SA_TRAFFIC_SOURCE,

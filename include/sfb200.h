@@ -108,6 +108,8 @@ int sfb_sa_prepare(const sfb_sa_weights* w, int C, int D, int Dm, void* workspac
 #define SFB_SA_NO_TCGEN05 1u /* run the mma.sync passes (sa_pass.cu) instead of the tcgen05 ones (sa_pass_tc.cu)  */
 #define SFB_SA_SPLIT_ON 2u   /* mma.sync first pass on warp pairs: force on ...                                   */
 #define SFB_SA_SPLIT_OFF 4u  /* ... / off (default: on when max_ctas caps the grid)                                */
+#define SFB_SA_XHAT_KEEP 8u  /* x^ ring stores keep their evict_last L2 policy under a capped grid (default: evict_first
+                                when the ring exceeds L2 and max_ctas caps the grid, i.e. the GPU is shared)          */
 
 /* Slot Attention forward for B independent frames (after sfb_sa_prepare on the same workspace).
  *   feats        [B, N, C]  fp32 (SFB_DTYPE_F32) or bf16 (SFB_DTYPE_BF16); rows contiguous, frame b at

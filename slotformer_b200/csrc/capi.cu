@@ -205,6 +205,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
     pp.cta_limited = cta_limited ? 1 : 0;
     pp.split = (flags & SFB_SA_SPLIT_ON) ? 1 : ((flags & SFB_SA_SPLIT_OFF) ? 0 : -1);
     pp.dbg = debug_switches();
+    pp.xhat_keep = (flags & SFB_SA_XHAT_KEEP) ? 1 : 0;
     // tcgen05 passes (C = 128) unless the caller asks for the mma.sync ones; q~ then lives in the operand layout
     const bool use_tc = !(flags & SFB_SA_NO_TCGEN05) && sfb::sa_pass_tc_supported(pp, C);
     up.qt_swz = use_tc ? 1 : 0;

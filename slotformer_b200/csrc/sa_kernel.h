@@ -53,6 +53,7 @@ struct SAPassParams {
     int cta_limited;           // the grid is capped below one CTA per SM (batch pipeline): the passes are SM-bound
     int split;                 // mma.sync first pass on warp pairs: 1 / 0 = forced on / off, -1 = when the grid is capped
     int dbg;                   // debug switches (debug build, SFB_DBG env): 1 = no proxy fence, 2 = no x^ store, 4 = skip LN+MMA work
+    int xhat_keep;             // SFB_SA_XHAT_KEEP: x^ stores stay evict_last even under a capped grid
     int reverse;               // tcgen05 passes: walk the items last-to-first (odd iterations: the pass starts on the x^
                                // tiles the previous pass touched last, which are still in L2)
 };

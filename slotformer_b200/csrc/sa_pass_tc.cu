@@ -462,7 +462,11 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
 #pragma unroll
         for (int j = 0; j < 8; ++j) xo[j] = (uint32_t)((j ^ (lane & 7)) << 4);
         const bool store_xhat = p.xhat != nullptr;
-        const uint64_t pol_x = l2_policy_evict_last();
+        // x^ stores: kept in L2 (evict_last) for the later pass to find -- unless the ring is far larger than L2 AND the
+        // GPU is shared with the rollout (capped grid): then 400 MB of evict_last lines only push the rollout's weight
+        // tiles out of L2
+        const bool ring_fits_l2 = (size_t)p.xhat_frames * p.n16 * TC_C * 2 <= ((size_t)48 << 20);
+        const uint64_t pol_x = (ring_fits_l2 || !p.cta_limited || p.xhat_keep) ? l2_policy_evict_last() : l2_policy_evict_first();
         TcProf pf(p, 2 + (lw >> 2), (lw & 3) == 0 && lane == 0);
         for (int n = lw; n < total_sub; n += 8) {
             static_assert(Cfg::NST == 8 && Cfg::NTB == 2, "one private stage per LayerNorm warp, one tile buffer per group");

@@ -19,6 +19,7 @@ _lib_debug = None
 SFB_SA_NO_TCGEN05 = 1
 SFB_SA_SPLIT_ON = 2
 SFB_SA_SPLIT_OFF = 4
+SFB_SA_XHAT_KEEP = 8
 SFB_RO_MMA_SYNC = 1
 
 SFB_DTYPE_F32 = 0
