@@ -503,6 +503,13 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
                             v[q * 32 + 4 * jj + e] = pack2(__uint_as_float(ww[e] << 16), __uint_as_float(ww[e] & 0xffff0000u));
                     }
             }
+            // pixels beyond N: a partially filled box is zero-filled by the TMA unit, but a sub-tile that starts beyond
+            // N is never loaded -- its stage holds whatever shared memory held (possibly Inf / NaN patterns, and
+            // 0 * NaN = NaN would reach the tensor cores): such rows are exact zeros
+            if (px >= N) {
+#pragma unroll
+                for (int i = 0; i < TC_C / 2; ++i) v[i] = pack2(0.f, 0.f);
+            }
             // statistics: plain in-thread sums over the row (4 independent chains each)
             f32x2 s2[4], q2[4];
 #pragma unroll
