@@ -176,6 +176,71 @@ __device__ __forceinline__ void ln_to_half_q(const float* h, unsigned char* out,
     }
 }
 
+// LayerNorm with 16 lanes per row (2 rows per warp, 16 rows per pass of the 8 warps) and every pass of the window
+// in flight at once: a lane owns the float4 chunks at features 4j + 64i of up to MAXP rows, whose loads, reductions
+// (4 shuffle steps each, issued for all rows together) and stores are independent chains.  ln_to_half_q (4 lanes per
+// row, 32 features per lane in one dependent chain) needed 2700 clocks for a 48-row window at 2 warps per
+// scheduler; the work per thread is the same here, the dependent chain is a quarter as long.
+template <int DMODEL, int HPAD, int MAXP, class Addr>
+__device__ __forceinline__ void ln_to_half_w(const float* h, unsigned char* out, Addr addr, int L, int Lp,
+                                             const float* gw, const float* gb, int warp, int lane, int rbegin = 0) {
+    constexpr int NV = DMODEL / 64, HS = DMODEL + HPAD;
+    const int j = lane & 15, rsub = lane >> 4;
+    float4 v[MAXP][NV];
+    float s[MAXP], q[MAXP];
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) {
+        const int r = rbegin + 16 * p + 2 * warp + rsub;
+        s[p] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[p][i] = (r < L) ? *reinterpret_cast<const float4*>(h + r * HS + 4 * j + 64 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s[p] += (v[p][i].x + v[p][i].y) + (v[p][i].z + v[p][i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1)
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) s[p] += __shfl_xor_sync(0xffffffffu, s[p], o);
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) {
+        const float mu = s[p] * (1.f / DMODEL);
+        q[p] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[p][i].x -= mu; v[p][i].y -= mu; v[p][i].z -= mu; v[p][i].w -= mu;
+            q[p] = fmaf(v[p][i].x, v[p][i].x, q[p]); q[p] = fmaf(v[p][i].y, v[p][i].y, q[p]);
+            q[p] = fmaf(v[p][i].z, v[p][i].z, q[p]); q[p] = fmaf(v[p][i].w, v[p][i].w, q[p]);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1)
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) q[p] += __shfl_xor_sync(0xffffffffu, q[p], o);
+    float4 g4[NV], b4[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        g4[i] = *reinterpret_cast<const float4*>(gw + 4 * j + 64 * i);
+        b4[i] = *reinterpret_cast<const float4*>(gb + 4 * j + 64 * i);
+    }
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) {
+        const int r = rbegin + 16 * p + 2 * warp + rsub;
+        if (r < Lp) {
+            const bool valid = r < L;
+            const float rstd = valid ? rsqrtf(q[p] * (1.f / DMODEL) + RO_LN_EPS) : 0.f;   // pad rows -> exact zeros
+            const float z = valid ? 1.f : 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                uint2 pk;
+                pk.x = pack_h2(fmaf(v[p][i].x * rstd, g4[i].x, b4[i].x * z), fmaf(v[p][i].y * rstd, g4[i].y, b4[i].y * z));
+                pk.y = pack_h2(fmaf(v[p][i].z * rstd, g4[i].z, b4[i].z * z), fmaf(v[p][i].w * rstd, g4[i].w, b4[i].w * z));
+                *reinterpret_cast<uint2*>(out + addr(r, 4 * j + 64 * i)) = pk;
+            }
+        }
+    }
+}
+
 // One (head, 16-query block) of softmax(Q K^T / sqrt(dh)) V.  Q/K/V live in `buf` (fp16, stride
 // ldb) at column offsets qcol/kcol/vcol; the result overwrites the Q block it came from.
 template <int DH, int NKB, class Addr>
@@ -281,9 +346,13 @@ __device__ __forceinline__ void attn_rows(unsigned char* buf, Addr addr, int qro
 // All (<= NMB) 16-query blocks of one head in one go: K/V fragments are loaded once and the
 // independent per-block chains (MMA -> shuffles -> exp2 -> MMA) interleave.  Used when the window
 // is short (NMB * NKB accumulators fit in registers).
-template <int DH, int NKB, int NMB, class Addr>
-__device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb, int qcol, int kcol, int vcol,
-                                          int L, int nkb, float sm_scale_log2, int lane, int qrow0 = 0) {
+// NKBV / NMBV >= 0: the number of key blocks holding a valid key / of query blocks is known at compile time (the
+// common window of a configuration): every guard below folds away and the per-block chains schedule as one block.
+template <int DH, int NKB, int NMB, int NKBV = -1, int NMBV = -1, class Addr>
+__device__ __forceinline__ void attn_head(unsigned char* buf, Addr addr, int nmb_rt, int qcol, int kcol, int vcol,
+                                          int L, int nkb_rt, float sm_scale_log2, int lane, int qrow0 = 0) {
+    const int nmb = NMBV >= 0 ? NMBV : nmb_rt;
+    const int nkb = NKBV >= 0 ? NKBV : nkb_rt;
     const int g = lane >> 2, t4 = lane & 3;
     const uint32_t b_u32 = smem_u32(buf);
     uint32_t qf[NMB][DH / 16][4];

@@ -512,7 +512,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                     // next layer's parameters: its buffer was last read before the barrier that ended the previous layer
                     if (lcount + 1 < total_layers) load_params((layer + 1) % p.layers, (lcount + 1) & 1);
                     mbar_wait_warp(&bars[RU_BAR_PAR + (lcount & 1)], (lcount >> 1) & 1u, lane);
-                    if (!(p.dbg & 64)) ln_to_half_q<DMODEL, RU_HPAD>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
+                    if (!(p.dbg & 64)) ln_to_half_w<DMODEL, RU_HPAD, NKB / 2>(h, xb, addr_s, L, Lp, l1w, l1b, warp, lane);
                 }
                 R.sync();
                 stamp();   // LN1
@@ -537,9 +537,18 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 if (Role::kCompute && !(p.dbg & 32)) {
                     if (NKB <= 6) {
                         // (the pruned last layer has nq / 16 query blocks starting at row rq0; same call, same code)
-                        for (int hh = warp; hh < p.heads; hh += RO_WARPS)
-                            attn_head<DH, (NKB <= 6 ? NKB : 2), (NKB <= 6 ? NKB / 2 : 1)>(
-                                yb, addr_s, nq >> 4, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb, 1.f, lane, rq0);
+                        constexpr int AKB = NKB <= 6 ? NKB : 2, AMB = NKB <= 6 ? NKB / 2 : 1;
+                        // the usual full layer (every query block, all but the last key block valid: L = 36 in a 48-row
+                        // window, L = 42 ...) runs the instantiation whose guards are compile-time constants
+                        const bool usual = (nq >> 4) == AMB && nkb == AKB - 1;
+                        for (int hh = warp; hh < p.heads; hh += RO_WARPS) {
+                            if (usual)
+                                attn_head<DH, AKB, AMB, AKB - 1, AMB>(
+                                    yb, addr_s, AMB, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, AKB - 1, 1.f, lane, rq0);
+                            else
+                                attn_head<DH, AKB, AMB>(
+                                    yb, addr_s, nq >> 4, hh * DH, DMODEL + hh * DH, 2 * DMODEL + hh * DH, L, nkb, 1.f, lane, rq0);
+                        }
                     } else {
                         const int nblk = nq >> 4;
                         for (int item = warp; item < p.heads * nblk; item += RO_WARPS) {
@@ -568,7 +577,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 R.fp.mark(14);
                 R.fp.mark(30);
                 if (Role::kCompute && !(p.dbg & 64))
-                    ln_to_half_q<DMODEL, RU_HPAD>(h, xb, addr_s, L, rq0 + nq, l2w, l2b, warp, lane, rq0);
+                    ln_to_half_w<DMODEL, RU_HPAD, NKB / 2>(h, xb, addr_s, L, rq0 + nq, l2w, l2b, warp, lane, rq0);
                 R.fp.mark(31);
                 R.sync();
                 R.fp.mark(32);
