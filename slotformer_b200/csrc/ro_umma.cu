@@ -128,10 +128,10 @@ struct BProducer {
                          nk * RU_TILE_BYTES, &ring.full[s], pol);
             }
     }
-    template <class Pre, class Epi>
+    template <int HF = 0, class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int, Pre, Epi) { emit(op); }
     // three-term product (W_hi X_hi + W_hi X_lo + W_lo X_hi): the hi tiles pass through the ring twice
-    template <class Pre, class Epi>
+    template <int HF = 0, class Pre, class Epi>
     __device__ __forceinline__ void gemm3(const UOp& hi, const UOp& lo, uint32_t, uint32_t, int, int, Pre, Epi) {
         emit(hi); emit(hi); emit(lo);
     }
@@ -203,11 +203,11 @@ struct BMma {
         if (elect_one()) umma_commit(bar);
         __syncwarp();
     }
-    template <class Pre, class Epi>
+    template <int HF = 0, class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t b_u32, int kblock_bytes, int ntok, Pre, Epi) {
         issue(op, b_u32, kblock_bytes, ntok, 0u, false, true);      // whole warp, uniform; one elected lane issues
     }
-    template <class Pre, class Epi>
+    template <int HF = 0, class Pre, class Epi>
     __device__ __forceinline__ void gemm3(const UOp& hi, const UOp& lo, uint32_t bhi_u32, uint32_t blo_u32, int kblock_bytes,
                                           int ntok, Pre, Epi) {
         issue(hi, bhi_u32, kblock_bytes, ntok, 0u, false, false);
@@ -261,10 +261,11 @@ struct BCompute {
     }
     // epi(feature, token8, values[8], pre(feature)): 8 consecutive tokens (token8 % 8 == 0) of one feature;
     // features of the warp's TMEM lane quadrant, one half of the tokens (warps w and w+4 share lanes)
-    template <class Pre, class Epi>
+    // HFIX > 0: tokens per warp known at compile time (the usual full window): the guards below fold away
+    template <int HFIX = 0, class Pre, class Epi>
     __device__ __forceinline__ void epi_tile(int t, uint32_t dcol, int ntok, Pre pre, Epi epi) {
         if (dbg & 4) return;
-        const int q = warp & 3, half = ntok >> 1, t0 = (warp >> 2) * half;
+        const int q = warp & 3, half = HFIX > 0 ? HFIX : (ntok >> 1), t0 = (warp >> 2) * half;
         const int f = t * 128 + 32 * q + lane;
         const float pv = pre(f);
         const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + dcol + (uint32_t)t0;
@@ -280,12 +281,13 @@ struct BCompute {
     // fp16 epilogue of one 128-feature tile: (acc + bias) [* qscale for features < nscale] [relu] -> operand
     // buffer `yb` (token rows, K-major swizzled).  16x256b TMEM loads give the stmatrix.trans fragment, so a
     // 16-feature x 16-token block is one store instruction instead of 8 scattered 2-byte stores per thread.
-    template <int HMAX>
+    template <int HMAX, bool FULL = false>
     __device__ __forceinline__ void epi_tile_h16(int t, uint32_t dcol, int ntok, const float* bias, bool relu,
                                                  float qscale, int nscale, unsigned char* yb, int kbb, int feat0 = 0,
                                                  int row0 = 0) {
         if (dbg & 4) return;
-        const int q = warp & 3, half = ntok >> 1, t0 = (warp >> 2) * half;   // HMAX >= half: tokens per warp
+        // HMAX >= half: tokens per warp; FULL: half == HMAX (the usual full window), guards fold at compile time
+        const int q = warp & 3, half = FULL ? HMAX : (ntok >> 1), t0 = (warp >> 2) * half;
         const uint32_t yb_u32 = smem_u32(yb);
         float v[2][HMAX / 2];        // [16-feature group][4 values per 8-token block]
 #pragma unroll
@@ -346,23 +348,28 @@ struct BCompute {
     template <int HMAX>
     __device__ __forceinline__ void gemm_h16(const UOp& op, uint32_t, int kbb, int ntok, const float* bias, float qscale,
                                              int nscale, unsigned char* yb, H16Ext x) {
+        const bool full = ntok == 2 * HMAX;
         for (int t = 0; t < op.ntile; ++t) {
             acc_wait(x.tbase + t);
-            epi_tile_h16<HMAX>(t, x.dcol0 + (uint32_t)(t * ntok), ntok, bias, false, qscale, nscale, yb, kbb, x.feat0, x.row0);
+            if (full) epi_tile_h16<HMAX, true>(t, x.dcol0 + (uint32_t)(t * ntok), ntok, bias, false, qscale, nscale, yb, kbb, x.feat0, x.row0);
+            else epi_tile_h16<HMAX, false>(t, x.dcol0 + (uint32_t)(t * ntok), ntok, bias, false, qscale, nscale, yb, kbb, x.feat0, x.row0);
         }
         tcgen05_fence_before();
     }
-    template <class Pre, class Epi>
+    // HF > 0: tokens per warp of the usual full window; that case runs the epilogue whose guards are constants
+    template <int HF = 0, class Pre, class Epi>
     __device__ __forceinline__ void gemm(const UOp& op, uint32_t, int, int ntok, Pre pre, Epi epi) {
+        const bool full = HF > 0 && ntok == 2 * HF;
         for (int t = 0; t < op.ntile; ++t) {
             acc_wait(t);
-            epi_tile(t, (uint32_t)(t * ntok), ntok, pre, epi);   // overlaps the MMAs of tile t+1
+            if (full) epi_tile<HF>(t, (uint32_t)(t * ntok), ntok, pre, epi);   // overlaps the MMAs of tile t+1
+            else epi_tile<0>(t, (uint32_t)(t * ntok), ntok, pre, epi);
         }
         tcgen05_fence_before();
     }
-    template <class Pre, class Epi>
+    template <int HF = 0, class Pre, class Epi>
     __device__ __forceinline__ void gemm3(const UOp& hi, const UOp&, uint32_t, uint32_t, int, int ntok, Pre pre, Epi epi) {
-        gemm(hi, 0u, 0, ntok, pre, epi);
+        gemm<HF>(hi, 0u, 0, ntok, pre, epi);
     }
     template <int HMAX>
     __device__ __forceinline__ void ffn(const FfnArgs& a) {
@@ -373,9 +380,11 @@ struct BCompute {
         }
         unsigned char* yb = a.yb;
         const int kbb = a.kbb;
+        const bool full = a.Lp == 2 * HMAX;
         for (int t = 0; t < nt; ++t) {
             acc_wait(t);
-            epi_tile_h16<HMAX>(t, (uint32_t)(t * a.Lp), a.Lp, a.b1 + a.f0, true, 1.f, 0, yb, kbb, 0, a.row0);
+            if (full) epi_tile_h16<HMAX, true>(t, (uint32_t)(t * a.Lp), a.Lp, a.b1 + a.f0, true, 1.f, 0, yb, kbb, 0, a.row0);
+            else epi_tile_h16<HMAX, false>(t, (uint32_t)(t * a.Lp), a.Lp, a.b1 + a.f0, true, 1.f, 0, yb, kbb, 0, a.row0);
             fp.mark(22);
             tcgen05_fence_before();
             fp.mark(23);
@@ -390,13 +399,16 @@ struct BCompute {
             float* h = a.h;
             const int d = a.d + RU_HPAD;
             for (int t2 = 0; t2 < dt; ++t2)
-                epi_tile(t2, a.acc2_col + (uint32_t)(t2 * a.Lp), a.Lp,
-                         [&](int f) { return a.b2[f]; },
-                         [&](int f, int t8, const float (&v)[8], float bi) {
-                             float* hf = h + (a.row0 + t8) * d + f;   // d: padded row stride
+            {
+                auto pre2 = [&](int f) { return a.b2[f]; };
+                auto epi2 = [&](int f, int t8, const float (&v)[8], float bi) {
+                    float* hf = h + (a.row0 + t8) * d + f;   // d: padded row stride
 #pragma unroll
-                             for (int i = 0; i < 8; ++i) hf[i * d] += v[i] + bi;
-                         });
+                    for (int i = 0; i < 8; ++i) hf[i * d] += v[i] + bi;
+                };
+                if (full) epi_tile<HMAX>(t2, a.acc2_col + (uint32_t)(t2 * a.Lp), a.Lp, pre2, epi2);
+                else epi_tile<0>(t2, a.acc2_col + (uint32_t)(t2 * a.Lp), a.Lp, pre2, epi2);
+            }
             tcgen05_fence_before();
         }
     }
@@ -471,7 +483,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
             {
                 const UOp op{p.w_in, Ds >> 6, 0, DMODEL >> 7, 0, Ds >> 6};
                 const UOp op_lo{p.w_in_lo, Ds >> 6, 0, DMODEL >> 7, 0, Ds >> 6};
-                R.gemm3(op, op_lo, x_u32, y_u32, kbb, Lp,
+                R.template gemm3<NKB * 4>(op, op_lo, x_u32, y_u32, kbb, Lp,
                        [&](int f) { return __ldg(p.b_in + f); },
                        [&](int f, int t8, const float (&v)[8], float bi) {
 #pragma unroll
@@ -564,7 +576,7 @@ __device__ __forceinline__ void run_rollout_b(Role& R, const ROParams& p, float*
                 // ---- h += O Wo^T + bo ----
                 {
                     const UOp op{ly.wo, DMODEL >> 6, 0, DMODEL >> 7, 0, DMODEL >> 6};
-                    R.gemm(op, y_u32 + (uint32_t)(rq0 * 128), kbb, nq,
+                    R.template gemm<NKB * 4>(op, y_u32 + (uint32_t)(rq0 * 128), kbb, nq,
                            [&](int f) { return s_bo[f]; },
                            [&](int f, int t8, const float (&v)[8], float bi) {
                                float* hf = h + (rq0 + t8) * (DMODEL + RU_HPAD) + f;
