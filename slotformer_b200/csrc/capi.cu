@@ -217,7 +217,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
         pp.frame0 = f0; pp.nframes = nf;
         // q~ of the initial slots
         up.do_update = 0; up.do_q = 1; up.first = 0; up.slots_prev = slots_in;
-        if ((e = sfb::sa_update_launch(up, C, di.sms, st)) != cudaSuccess) return cuda_err(e);
+        if ((e = sfb::sa_update_launch(up, C, di.sms, st, cta_limited)) != cudaSuccess) return cuda_err(e);
         g_launches.fetch_add(1);
         for (int it = 0; it < n_iter; ++it) {
             const bool last = (it == n_iter - 1);
@@ -232,7 +232,7 @@ int sfb_sa_forward(const void* feats, int feat_dtype, int64_t feat_batch_stride,
             g_launches.fetch_add(1);
             up.do_update = 1; up.do_q = last ? 0 : 1; up.first = (it == 0);
             up.slots_prev = (it == 0) ? slots_in : slots_out;
-            if ((e = sfb::sa_update_launch(up, C, di.sms, st)) != cudaSuccess) return cuda_err(e);
+            if ((e = sfb::sa_update_launch(up, C, di.sms, st, cta_limited)) != cudaSuccess) return cuda_err(e);
             g_launches.fetch_add(1);
         }
     }

@@ -85,7 +85,7 @@ cudaError_t sa_pass_split_launch(const SAPassParams& p, int sms, cudaStream_t st
 // tcgen05 passes (sa_pass_tc.cu): C = 128; q~ must be in the swizzled operand layout (SAUpdateParams::qt_swz)
 bool sa_pass_tc_supported(const SAPassParams& p, int C);
 cudaError_t sa_pass_tc_launch(const SAPassParams& p, bool first, int sms, cudaStream_t st);
-cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st);
+cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st, bool capped = false);
 // encoder tail (enc_tail.cu)
 size_t enc_tail_workspace_bytes();
 cudaError_t enc_tail_prep_launch(const float* pos_w, const float* pos_b, const float* ln_w, const float* ln_b,

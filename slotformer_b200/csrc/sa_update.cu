@@ -221,7 +221,9 @@ __device__ __forceinline__ void ln_rows_split(const float* src, int lds, __half*
     }
 }
 
-template <int C, int NMB>
+// NSTCAP: ring depth limit.  8 = as deep as shared memory allows (one CTA per SM); 3 = a 48 KB ring, so that two
+// CTAs of the 16-row variant fit one SM (used when the grid is capped: twice the CTA slots, one wave instead of 32-row CTAs)
+template <int C, int NMB, int NSTCAP = 8>
 struct UpdCfg {
     static constexpr int D = C, DM = 2 * C, ROWS = 16 * NMB;
     static constexpr int LDA = C + 8, LDH = DM + 8, LDS = D + 4;
@@ -234,15 +236,15 @@ struct UpdCfg {
     static constexpr int OFF_BARS = OFF_PAR + PAR_FLOATS * 4;
     static constexpr int OFF_RING = (OFF_BARS + 2 * 8 * 8 + 1023) / 1024 * 1024;
     static constexpr int NST_FIT = (232448 - OFF_RING) / PAIR_BYTES;
-    static constexpr int NST = NST_FIT > 8 ? 8 : NST_FIT;
+    static constexpr int NST = NST_FIT > NSTCAP ? NSTCAP : NST_FIT;
     static_assert(NST >= 3, "update kernel: shared memory budget");
     static constexpr int SMEM = OFF_RING + NST * PAIR_BYTES;
 };
 
-template <int C, int NMB, class Role>
+template <int C, int NMB, int NSTCAP, class Role>
 __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, unsigned char* smem, int tid,
                                            int warp, int lane) {
-    using Cfg = UpdCfg<C, NMB>;
+    using Cfg = UpdCfg<C, NMB, NSTCAP>;
     constexpr int D = Cfg::D, DM = Cfg::DM, ROWS = Cfg::ROWS, LDA = Cfg::LDA, LDH = Cfg::LDH, LDS = Cfg::LDS;
     __half* a_hi = reinterpret_cast<__half*>(smem + Cfg::OFF_A);
     __half* a_lo = a_hi + ROWS * LDA;
@@ -489,9 +491,9 @@ __device__ __forceinline__ void run_update(Role& R, const SAUpdateParams& p, uns
     }
 }
 
-template <int C, int NMB>
-__global__ void __launch_bounds__(UPD_THREADS + 32, 1) sa_update_kernel(const SAUpdateParams p) {
-    using Cfg = UpdCfg<C, NMB>;
+template <int C, int NMB, int NSTCAP = 8>
+__global__ void __launch_bounds__(UPD_THREADS + 32, NSTCAP < 8 ? 2 : 1) sa_update_kernel(const SAUpdateParams p) {
+    using Cfg = UpdCfg<C, NMB, NSTCAP>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
@@ -516,12 +518,12 @@ __global__ void __launch_bounds__(UPD_THREADS + 32, 1) sa_update_kernel(const SA
     if (warp == UPD_WARPS) {
         if (lane == 0) {
             UProducer P{ring, 0u, l2_policy_evict_last()};
-            run_update<C, NMB>(P, p, smem, tid, warp, lane);
+            run_update<C, NMB, NSTCAP>(P, p, smem, tid, warp, lane);
         }
         return;
     }
     UConsumer<NMB> Cn{ring, 0u, warp, lane};
-    run_update<C, NMB>(Cn, p, smem, tid, warp, lane);
+    run_update<C, NMB, NSTCAP>(Cn, p, smem, tid, warp, lane);
 }
 
 // ============================================================================================
@@ -569,10 +571,10 @@ cudaError_t sa_prep_launch(const float* wq, const float* wk, const float* wv, co
     return cudaGetLastError();
 }
 
-template <int C, int NMB>
+template <int C, int NMB, int NSTCAP = 8>
 static cudaError_t update_launch_t(const SAUpdateParams& p, cudaStream_t st) {
-    using Cfg = UpdCfg<C, NMB>;
-    auto kern = sa_update_kernel<C, NMB>;
+    using Cfg = UpdCfg<C, NMB, NSTCAP>;
+    auto kern = sa_update_kernel<C, NMB, NSTCAP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
     const int grid = (p.nframes * p.K + Cfg::ROWS - 1) / Cfg::ROWS;      // dense rows: frame R / K, slot R % K
@@ -580,12 +582,15 @@ static cudaError_t update_launch_t(const SAUpdateParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st) {
+cudaError_t sa_update_launch(const SAUpdateParams& p, int C, int sms, cudaStream_t st, bool capped) {
     // 16*NMB rows per CTA.  A CTA's time grows with NMB (about 13 us + 14 us per 16 rows), every CTA streams the
     // whole weight set, so: the smallest NMB whose grid still fits one wave of the SMs this call may use.
     const int need = (p.nframes * p.K + sms - 1) / sms;           // rows per CTA for a single wave
     if (C == 128) {
         if (need <= 16) return update_launch_t<128, 1>(p, st);
+        // capped grid (the batch pipeline): two 16-row CTAs per SM (48 KB weight ring each) still make one wave where
+        // 32-row CTAs would be needed otherwise (41 -> ~30 us per launch at 84 SMs)
+        if (need <= 32 && capped) return update_launch_t<128, 1, 3>(p, st);
         if (need <= 32) return update_launch_t<128, 2>(p, st);
         if (need <= 48) return update_launch_t<128, 3>(p, st);
         return update_launch_t<128, 4>(p, st);
