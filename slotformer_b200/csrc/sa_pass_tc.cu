@@ -320,33 +320,30 @@ __device__ __forceinline__ void tc_softmax_role(const SAPassParams& p, unsigned 
             tmem_ld_wait();
             pf.mark(3, t);
             const int px = (chunk * it.tpi + j) * TC_TILE_PX + row;
-            float e[8], m = -INFINITY;
+            // one thread's softmax over the <= 8 slots is a dependent chain on a warp that has its scheduler to itself:
+            // tree-shaped max / sum (depth 3 instead of 8), one ex2.approx per slot (slots >= K sit at -inf and come
+            // out as exact zeros), the 1024 scale folded into the normaliser
+            float e[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                e[s] = (lg[s] + lg[8 + s]) + lb[s];
-                if (s < K) m = fmaxf(m, e[s]);
-            }
-            float sum = 0.f;
+            for (int s = 0; s < 8; ++s) e[s] = (s < K) ? (lg[s] + lg[8 + s]) + lb[s] : -INFINITY;
+            const float m = fmaxf(fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])), fmaxf(fmaxf(e[4], e[5]), fmaxf(e[6], e[7])));
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                e[s] = (s < K) ? exp2f(e[s] - m) : 0.f;
-                sum += e[s];
-            }
-            const float inv = (px < N) ? __fdividef(1.f, sum) : 0.f;
-#pragma unroll
-            for (int s = 0; s < 8; ++s) e[s] *= inv;
+            for (int s = 0; s < 8; ++s) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[s]) : "f"(e[s] - m));
+            const float sum = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            const float inv = (px < N) ? __fdividef(TC_PSCALE, sum) : 0.f;       // 1024 / sum
             if (p.seg_mask != nullptr && px < N) {
                 float* mk = p.seg_mask + (size_t)f * K * N + px;
+                const float inv1 = inv * (1.f / TC_PSCALE);
 #pragma unroll
                 for (int s = 0; s < 8; ++s)
-                    if (s < K) mk[(size_t)s * N] = e[s];
+                    if (s < K) mk[(size_t)s * N] = e[s] * inv1;
             }
             uint4 pk;
             {
-                const __half2 h0 = __floats2half2_rn(e[0] * TC_PSCALE, e[1] * TC_PSCALE);
-                const __half2 h1 = __floats2half2_rn(e[2] * TC_PSCALE, e[3] * TC_PSCALE);
-                const __half2 h2 = __floats2half2_rn(e[4] * TC_PSCALE, e[5] * TC_PSCALE);
-                const __half2 h3 = __floats2half2_rn(e[6] * TC_PSCALE, e[7] * TC_PSCALE);
+                const __half2 h0 = __floats2half2_rn(e[0] * inv, e[1] * inv);
+                const __half2 h1 = __floats2half2_rn(e[2] * inv, e[3] * inv);
+                const __half2 h2 = __floats2half2_rn(e[4] * inv, e[5] * inv);
+                const __half2 h3 = __floats2half2_rn(e[6] * inv, e[7] * inv);
                 // column sums from the ROUNDED values (numerator and denominator of the update see the same a)
                 const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
                 cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y;
