@@ -21,7 +21,7 @@ def timed(fn, n=10):
 SA = [('sa_cfg1', 4 * 6, False), ('sa_cfg2', 64 * 6, False), ('sa_cfg3', 32 * 6, True), ('sa_cfg4', 16 * 4, False)]
 RO = [('ro_cfg2', 64), ('ro_cfg3', 32), ('ro_cfg4', 16), ('ro_cfg5', 256), ('ro_physion', 16)]
 with torch.no_grad():
-    for name, frames, bf16 in SA:
+    for name, frames, bf16 in ([] if os.environ.get('SKIP_SA') else SA):
         c, w, _, _ = cases.sa_case(name)
         m = sa_module(c, w, dev, mask=c['mask'])
         f = torch.randn((frames, c['N'], c['C']), device=dev)

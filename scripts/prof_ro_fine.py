@@ -6,10 +6,20 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden
 import numpy as np, torch, bench
 from slotformer_b200 import engine
 from slotformer_b200.video_prediction.models import SlotRollouter
-dev = 'cuda:0'; WL = bench.WL; lib = engine.use_debug_library()   # -DSFB_DEBUG build: timeline hook + SFB_DBG switches
-_, ro_w = bench.make_weights()
-ro = SlotRollouter(WL['K'], WL['D'], WL['T_in'], d_model=WL['d'], num_layers=WL['layers'], num_heads=WL['heads'], ffn_dim=WL['F'])
-ro.load_state_dict({k: torch.from_numpy(v) for k, v in ro_w.items()}, strict=False); ro = ro.to(dev).eval()
+dev = 'cuda:0'; WL = dict(bench.WL); lib = engine.use_debug_library()   # -DSFB_DEBUG build: timeline hook + SFB_DBG switches
+CASE = os.environ.get('RO_CASE')          # e.g. RO_CASE=ro_cfg3: a tests/golden/cases.py rollout case instead of the bench workload
+if CASE:
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import cases
+    from helpers import ro_module
+    c, w, hist = cases.ro_case(CASE)
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', CASE + '.npz'))
+    ro = ro_module(c, w, dev, enc_t_pe=g['enc_t_pe'])
+    WL.update(B=int(os.environ.get('RO_B', 32)), T_in=c['T_h'], K=c['K'], D=c['Ds'], layers=c['layers'], T_out=min(c['pred_len'], 10))
+else:
+    _, ro_w = bench.make_weights()
+    ro = SlotRollouter(WL['K'], WL['D'], WL['T_in'], d_model=WL['d'], num_layers=WL['layers'], num_heads=WL['heads'], ffn_dim=WL['F'])
+    ro.load_state_dict({k: torch.from_numpy(v) for k, v in ro_w.items()}, strict=False); ro = ro.to(dev).eval()
 x = torch.randn((WL['B'], WL['T_in'], WL['K'], WL['D']), device=dev)
 cap = 8192
 buf = torch.zeros(cap, dtype=torch.int64, device=dev)
