@@ -223,6 +223,66 @@ int sfb_rollout_forward(const float* hist, float* pred_out, const sfb_ro_weights
                         void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* SAVi slot transition (next row f3): predictor + kernel_dist_layer + sample   */
+/* ------------------------------------------------------------------------- */
+/* The per-frame glue between two Slot Attention calls of StoSAVi.encode (base_slots/models/savi.py:393-410):
+ *   latents = predictor(prev_slots)        predictor.py:20-44 TransformerPredictor | :47-74 ResidualMLPPredictor,
+ *                                          optionally inside predictor.py:76-113 RNNPredictorWrapper (LSTM, 1 layer)
+ *   dist    = kernel_dist_layer(latents)   savi.py:200-212
+ *   slots0  = mu + noise * exp(logvar/2)   savi.py:355-363 (noise == NULL: slots0 = mu, kld_method 'none')
+ * as ONE kernel launch (a thread-block cluster per clip; csrc/transition.cu).  Field names = state_dict keys of
+ * `predictor.` / `kernel_dist_layer.`; unused pointers stay NULL. */
+#define SFB_TR_NONE 0        /* no predictor: latents = input rows (first frame: init_latents, prev_clip_stride 0) */
+#define SFB_TR_TRANSFORMER 1 /* [base_predictor.]transformer_encoder.layers.<i>.* */
+#define SFB_TR_MLP 2         /* [base_predictor.]ln.*, mlp.0.*, mlp.2.*  (channels [D, mlp_hidden, D]) */
+#define SFB_TR_MAX_LAYERS 4
+
+typedef struct sfb_tr_weights {
+    int pred_type;  /* SFB_TR_* */
+    int num_layers; /* transformer layers */
+    int num_heads;
+    int ffn_dim;
+    int norm_first;
+    sfb_ro_layer layers[SFB_TR_MAX_LAYERS];
+    int mlp_hidden;
+    const float* ln_weight;    /* [D] */
+    const float* ln_bias;      /* [D] */
+    const float* mlp_0_weight; /* [mlp_hidden, D] */
+    const float* mlp_0_bias;
+    const float* mlp_2_weight; /* [D, mlp_hidden] */
+    const float* mlp_2_bias;
+    int rnn_hidden;                     /* 0: no RNNPredictorWrapper */
+    const float* rnn_weight_ih_l0;      /* [4H, D]  gate order i, f, g, o */
+    const float* rnn_weight_hh_l0;      /* [4H, H]  */
+    const float* rnn_bias_ih_l0;        /* [4H]     */
+    const float* rnn_bias_hh_l0;        /* [4H]     */
+    const float* out_projector_weight;  /* [D, H]   */
+    const float* out_projector_bias;    /* [D]      */
+    int kernel_mlp;                     /* 1: Linear -> LayerNorm -> ReLU -> Linear;  0: Linear */
+    const float* kernel_dist_0_weight;  /* [2D, D]  */
+    const float* kernel_dist_0_bias;
+    const float* kernel_dist_1_weight;  /* LayerNorm [2D] (kernel_mlp) */
+    const float* kernel_dist_1_bias;
+    const float* kernel_dist_3_weight;  /* [2D, 2D] (kernel_mlp) */
+    const float* kernel_dist_3_bias;
+} sfb_tr_weights;
+
+/* Bytes of device workspace for the k-major fp32 copies of the weights (0: unsupported structure / sizes). */
+size_t sfb_transition_workspace_bytes(const sfb_tr_weights* w, int D);
+/* Re-pack the weights into `workspace`; call again whenever a weight tensor changed. */
+int sfb_transition_prepare(const sfb_tr_weights* w, int D, void* workspace, size_t workspace_bytes, void* stream);
+/* One transition for B clips of K <= 8 slots (D = slot size):
+ *   prev [.., K, D] fp32 rows of clip b at prev + b * prev_clip_stride (floats; 0 = the same K rows for every clip)
+ *   use_predictor 0: latents = prev (first frame);  1: latents = predictor(prev)
+ *   h_in / c_in  [B*K, H] LSTM state before the step (NULL = zeros), h_out / c_out [B*K, H] after it (rnn_hidden > 0)
+ *   noise        NULL or [B, K, D]      dist_out [B, K, 2D]      slots_out [B, K, D]
+ * Supported: D % 4 == 0, every layer width (3D, ffn_dim, mlp_hidden, 4H, D + H, 2D) <= 1024 and a multiple of 32. */
+int sfb_transition_forward(const sfb_tr_weights* w, int D, int B, int K, const float* prev, long long prev_clip_stride,
+                           int use_predictor, const float* h_in, const float* c_in, const float* noise,
+                           float* dist_out, float* slots_out, float* h_out, float* c_out, const void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Decoder epilogue (next row f2): the tail of StoSAVi.decode + postproc_mask   */
 /* ------------------------------------------------------------------------- */
 /* Everything after the deconvolution stack of the spatial-broadcast decoder (base_slots/models/savi.py:519-523):

@@ -15,7 +15,8 @@ from torch.nn import functional as F
 from ...compat.nerv.models import conv_norm_act, deconv_norm_act, deconv_out_shape
 from ...compat.nerv.training import BaseModel
 from .predictor import ResidualMLPPredictor, RNNPredictorWrapper, TransformerPredictor
-from ...engine import ENC_TAIL_KEYS, SFB_SA_NO_TCGEN05, EncoderTailEngine, FeatureTiles
+from ...engine import (ENC_TAIL_KEYS, RO_LAYER_KEYS, SFB_SA_NO_TCGEN05, SFB_TR_MLP, SFB_TR_TRANSFORMER, TR_MAX_LAYERS,
+                       EncoderTailEngine, FeatureTiles, TransitionEngine)
 from .slot_attention import SlotAttention
 from .utils import SoftPositionEmbed, assert_shape, torch_cat
 
@@ -207,16 +208,131 @@ class StoSAVi(BaseModel):
         return self._enc_tail_engine.forward(x, {k: named[k].detach() for k in ENC_TAIL_KEYS}, self.enc_out_channels,
                                              max_ctas=self.slot_attention.max_ctas)
 
+    # -- predictor -> kernel_dist_layer -> sample as ONE kernel per frame -------------------
+    # The slot transition between two Slot Attention calls (reference savi.py:393-410 with predictor.py:20-113) is
+    # ~40 stock launches on [B*K, D] activations; in inference it runs as one cluster-per-clip kernel
+    # (csrc/transition.cu).  Structures outside the kernel's envelope keep the stock modules.
+    fuse_transition = True
+
+    def _transition_spec(self):
+        """Structure + weights of ``predictor`` / ``kernel_dist_layer`` for sfb_transition_forward, or None."""
+        D = self.slot_size
+        W = {}
+        spec = dict(pred_type=0, num_layers=0, num_heads=0, ffn_dim=0, norm_first=True, mlp_hidden=0, rnn_hidden=0,
+                    weights=W)
+
+        def is_ln(m, width):
+            return isinstance(m, nn.LayerNorm) and m.elementwise_affine and m.bias is not None and m.eps == 1e-5 \
+                and tuple(m.normalized_shape) == (width,)
+
+        def is_lin(m, cin, cout):
+            return isinstance(m, nn.Linear) and m.bias is not None and m.in_features == cin and m.out_features == cout
+
+        core = self.predictor
+        if isinstance(core, RNNPredictorWrapper):
+            rnn = core.rnn
+            if not isinstance(rnn, nn.LSTM) or rnn.num_layers != 1 or rnn.bidirectional or not rnn.bias \
+                    or rnn.proj_size != 0 or rnn.input_size != D or not is_lin(core.out_projector, rnn.hidden_size, D):
+                return None
+            spec['rnn_hidden'] = rnn.hidden_size
+            for k in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0'):
+                W['rnn.' + k] = getattr(rnn, k).detach()
+            W['out_projector.weight'] = core.out_projector.weight.detach()
+            W['out_projector.bias'] = core.out_projector.bias.detach()
+            core = core.base_predictor
+        if isinstance(core, TransformerPredictor):
+            enc = core.transformer_encoder
+            layers = list(enc.layers)
+            l0 = layers[0]
+            if enc.norm is not None or not 1 <= len(layers) <= TR_MAX_LAYERS:
+                return None
+            for i, ly in enumerate(layers):
+                att = ly.self_attn
+                relu = ly.activation is F.relu or getattr(ly, 'activation_relu_or_gelu', 0) == 1
+                if not relu or att.embed_dim != D or att.in_proj_weight is None or att.in_proj_bias is None \
+                        or att.bias_k is not None or att.add_zero_attn or ly.norm_first != l0.norm_first \
+                        or att.num_heads != l0.self_attn.num_heads or not is_ln(ly.norm1, D) or not is_ln(ly.norm2, D) \
+                        or not is_lin(ly.linear1, D, l0.linear1.out_features) or not is_lin(ly.linear2, l0.linear1.out_features, D):
+                    return None
+                for k in RO_LAYER_KEYS:
+                    obj = ly
+                    for part in k.split('.'):
+                        obj = getattr(obj, part)
+                    W[f'layers.{i}.{k}'] = obj.detach()
+            spec.update(pred_type=SFB_TR_TRANSFORMER, num_layers=len(layers), num_heads=l0.self_attn.num_heads,
+                        ffn_dim=l0.linear1.out_features, norm_first=bool(l0.norm_first))
+        elif isinstance(core, ResidualMLPPredictor):
+            mlp = core.mlp
+            if len(mlp) != 3 or not isinstance(mlp[1], nn.ReLU) or not is_ln(core.ln, D) \
+                    or not isinstance(mlp[0], nn.Linear) or not is_lin(mlp[0], D, mlp[0].out_features) \
+                    or not is_lin(mlp[2], mlp[0].out_features, D):
+                return None
+            spec.update(pred_type=SFB_TR_MLP, mlp_hidden=mlp[0].out_features, norm_first=bool(core.norm_first))
+            for name, m in (('ln', core.ln), ('mlp.0', mlp[0]), ('mlp.2', mlp[2])):
+                W[name + '.weight'] = m.weight.detach()
+                W[name + '.bias'] = m.bias.detach()
+        else:
+            return None
+        kd = self.kernel_dist_layer
+        if len(kd) == 4 and is_lin(kd[0], D, 2 * D) and is_ln(kd[1], 2 * D) and isinstance(kd[2], nn.ReLU) \
+                and is_lin(kd[3], 2 * D, 2 * D):
+            spec['kernel_mlp'] = True
+            mods = (('0', kd[0]), ('1', kd[1]), ('3', kd[3]))
+        elif len(kd) == 1 and is_lin(kd[0], D, 2 * D):
+            spec['kernel_mlp'] = False
+            mods = (('0', kd[0]),)
+        else:
+            return None
+        for name, m in mods:
+            W[f'kernel_dist.{name}.weight'] = m.weight.detach()
+            W[f'kernel_dist.{name}.bias'] = m.bias.detach()
+        return spec
+
+    def _transition_fusable(self, feats):
+        if not (self.fuse_transition and feats.is_cuda and not self.training and not torch.is_grad_enabled()
+                and self.dtype == torch.float32 and self.num_slots <= 8):
+            return None
+        # one cluster (>= 1 CTA) per clip, a single wave: beyond that many clips the stock GEMMs on [B*K, D] win
+        if feats.shape[0] > torch.cuda.get_device_properties(feats.device).multi_processor_count:
+            return None
+        spec = self._transition_spec()
+        if spec is None or any(not t.is_cuda or t.dtype != torch.float32 for t in spec['weights'].values()) \
+                or not TransitionEngine.supported(spec, self.slot_size):
+            return None
+        return spec
+
+    def _transition(self, spec, prev_slots, B):
+        """(kernel_dist, initial slots) of the next frame from the previous frame's slots: one kernel launch."""
+        if '_transition_engine' not in self.__dict__:
+            self.__dict__['_transition_engine'] = TransitionEngine()
+        pred = self.predictor
+        rnn = spec['rnn_hidden'] > 0 and prev_slots is not None
+        state = pred.hidden_state if rnn else None
+        noise = None
+        if self.kld_method != 'none':
+            noise = torch.randn((B, self.num_slots, self.slot_size), dtype=torch.float32, device=self.init_latents.device)
+        prev = self.init_latents.detach() if prev_slots is None else prev_slots
+        dist, init, new = self._transition_engine.forward(spec, prev, prev_slots is not None, B, state, noise)
+        if rnn:
+            pred.hidden_state = (new[0].unsqueeze(0), new[1].unsqueeze(0))
+            pred.step += 1
+        return dist, init
+
     def _frame_loop(self, feats, prev_slots):
         """The serial per-frame chain (reference savi.py:393-410): predictor -> kernel_dist_layer -> sample ->
         Slot Attention, T times.  feats [B, T, N, C] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D])."""
         B, T = feats.shape[:2]
-        start = self.init_latents.repeat(B, 1, 1)
+        spec = self._transition_fusable(feats)
+        start = self.init_latents.repeat(B, 1, 1) if spec is None else None
         dists, slots = [], []
         for t in range(T):                                  # frames are a serial chain
-            latents = start if prev_slots is None else self.predictor(prev_slots)
-            dist = self.kernel_dist_layer(latents)
-            prev_slots = self.slot_attention(feats[:, t], self._sample_dist(dist))   # hot path 1
+            if spec is not None:
+                dist, init = self._transition(spec, prev_slots, B)
+            else:
+                latents = start if prev_slots is None else self.predictor(prev_slots)
+                dist = self.kernel_dist_layer(latents)
+                init = self._sample_dist(dist)
+            prev_slots = self.slot_attention(feats[:, t], init)   # hot path 1
             dists.append(dist)
             slots.append(prev_slots)
         return torch.stack(dists, dim=1), torch.stack(slots, dim=1)

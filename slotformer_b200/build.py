@@ -22,9 +22,9 @@ LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsfb200.so')
 LIB_DEBUG = os.path.join(LIBDIR, 'libsfb200_debug.so')
 SOURCES = ["capi.cu", "sa_pass.cu", "sa_pass_tc.cu", "enc_tail.cu", "sa_update.cu", "ro_kernel.cu", "ro_umma.cu", "ro_pack.cu", "decode_combine.cu",
-           "sa_pass_split.cu"]
+           "sa_pass_split.cu", "transition.cu"]
 DEBUG_SOURCES = ["umma_test.cu"]
-HEADERS = ['common.cuh', 'sa_kernel.h', 'ro_kernel.h', 'ro_attn.cuh', 'umma.cuh', 'decode_kernel.h', os.path.join('..', '..', 'include', 'sfb200.h')]
+HEADERS = ['common.cuh', 'sa_kernel.h', 'ro_kernel.h', 'ro_attn.cuh', 'umma.cuh', 'decode_kernel.h', 'transition_kernel.h', os.path.join('..', '..', 'include', 'sfb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '--use_fast_math', '-Xptxas', '-v']
 # --use_fast_math would change expf/division semantics in the slot update; keep IEEE there

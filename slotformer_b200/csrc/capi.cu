@@ -4,6 +4,7 @@
 #include "sa_kernel.h"
 #include "ro_kernel.h"
 #include "decode_kernel.h"
+#include "transition_kernel.h"
 
 #include <atomic>
 #include <cstring>
@@ -493,6 +494,310 @@ int sfb_postproc_mask(const float* masks, long long* seg, void* slot_max_ws, int
             return cuda_err(e);
         g_launches.fetch_add(2);
     }
+    return SFB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// SAVi slot transition (section 8 f3): program + weight layout for csrc/transition.cu
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct TrLinear { long long w, b; int Kd, N; };                 // blob offsets (floats)
+struct TrNorm { long long g, b; int W; };
+struct TrLayout {
+    TrLinear qkv[SFB_TR_MAX_LAYERS], wo[SFB_TR_MAX_LAYERS], w1[SFB_TR_MAX_LAYERS], w2[SFB_TR_MAX_LAYERS];
+    TrNorm n1[SFB_TR_MAX_LAYERS], n2[SFB_TR_MAX_LAYERS];
+    TrNorm mlp_ln; TrLinear mlp0, mlp2;
+    TrLinear gates, outp;
+    TrLinear kd0, kd3; TrNorm kdn;
+    long long floats, vec_floats;
+};
+
+inline long long tr_alloc(long long* top, long long n) { const long long o = *top; *top += (n + 3) & ~3LL; return o; }
+
+// 0 = ok; the layout depends on the structure fields and D only (prepare and forward agree on it)
+int tr_layout(const sfb_tr_weights* w, int D, TrLayout* L) {
+    if (!w || D < 32 || D > 512 || (D % 32)) return SFB_E_BAD_SHAPE;
+    // every vector (biases, LayerNorm affine) first, contiguous: the kernel stages that region in shared memory;
+    // two passes: the first one only sizes the vector region
+    bool ok = true;
+    long long vec_total = 0, top = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        long long vtop = 0;
+        top = vec_total;
+        auto lin = [&](TrLinear* t, int Kd, int N) {
+            t->Kd = Kd; t->N = N;
+            t->w = tr_alloc(&top, (long long)Kd * N);
+            t->b = tr_alloc(&vtop, N);
+            return (N % 32 == 0) && N <= sfb::TR_MAX_WIDTH && Kd <= sfb::TR_MAX_WIDTH && Kd >= 8;
+        };
+        auto norm = [&](TrNorm* t, int W) { t->W = W; t->g = tr_alloc(&vtop, W); t->b = tr_alloc(&vtop, W); };
+        ok = true;
+        if (w->pred_type == SFB_TR_TRANSFORMER) {
+            if (w->num_layers < 1 || w->num_layers > SFB_TR_MAX_LAYERS) return SFB_E_BAD_SHAPE;
+            if (w->num_heads < 1 || w->num_heads > 16 || D % w->num_heads) return SFB_E_BAD_SHAPE;
+            for (int l = 0; l < w->num_layers; ++l) {
+                ok &= lin(&L->qkv[l], D, 3 * D);
+                ok &= lin(&L->wo[l], D, D);
+                ok &= lin(&L->w1[l], D, w->ffn_dim);
+                ok &= lin(&L->w2[l], w->ffn_dim, D);
+                norm(&L->n1[l], D);
+                norm(&L->n2[l], D);
+            }
+        } else if (w->pred_type == SFB_TR_MLP) {
+            norm(&L->mlp_ln, D);
+            ok &= lin(&L->mlp0, D, w->mlp_hidden);
+            ok &= lin(&L->mlp2, w->mlp_hidden, D);
+        } else if (w->pred_type != SFB_TR_NONE) {
+            return SFB_E_BAD_SHAPE;
+        }
+        if (w->rnn_hidden > 0) {
+            if (w->pred_type == SFB_TR_NONE || 2 * w->rnn_hidden > sfb::TR_MAX_WIDTH) return SFB_E_BAD_SHAPE;
+            ok &= lin(&L->gates, D + w->rnn_hidden, 4 * w->rnn_hidden);
+            ok &= lin(&L->outp, w->rnn_hidden, D);
+        }
+        ok &= lin(&L->kd0, D, 2 * D);
+        if (w->kernel_mlp) {
+            norm(&L->kdn, 2 * D);
+            ok &= lin(&L->kd3, 2 * D, 2 * D);
+        }
+        vec_total = vtop;
+    }
+    if (vec_total > sfb::TR_MAX_VEC) return SFB_E_BAD_SHAPE;
+    L->vec_floats = vec_total;
+    L->floats = top;
+    return ok ? SFB_OK : SFB_E_BAD_SHAPE;
+}
+
+// The program of one transition.  LINEAR steps end in a cluster barrier and write their result into the buffer of every
+// CTA of the cluster: their destination must not have been read or written by any step since the previous barrier
+// (a slower CTA may still be there).  `touched` tracks that; a violation is a bug in this builder, reported as BAD_SHAPE.
+struct TrBuilder {
+    sfb::TrParams* p;
+    unsigned touched = 0, reserved = 0;
+    int err = 0;
+    void push(int code, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0, int a4 = 0, int a5 = 0, int a6 = 0) {
+        if (p->nops >= sfb::TR_MAX_OPS) { err = 1; return; }
+        sfb::TrOp& o = p->ops[p->nops++];
+        o.code = code; o.a[0] = a0; o.a[1] = a1; o.a[2] = a2; o.a[3] = a3; o.a[4] = a4; o.a[5] = a5; o.a[6] = a6;
+    }
+    int pick(unsigned live) {
+        for (int i = 0; i < sfb::TR_NBUF; ++i) if (!(((touched | live | reserved) >> i) & 1u)) return i;
+        err = 1; return 0;
+    }
+    void load(int buf, int in, int W, int rstride, int foff, long long cstride, int flags) {
+        push(sfb::TR_LOAD, buf, in, W, rstride, foff, (int)cstride, flags); touched |= 1u << buf;
+    }
+    void ln(int src, int dst, const TrNorm& n, int flags) {
+        push(sfb::TR_LN, src, dst, n.W, (int)n.g, (int)n.b, flags); touched |= (1u << src) | (1u << dst);
+    }
+    // src2 >= 0: operand rows k >= ksplit come from buffer src2 at feature offset off2
+    void linear(int src, int dst, const TrLinear& t, int flags, int src2 = -1, int off2 = 0, int ksplit = 0) {
+        if (src == dst || src2 == dst || ((touched >> dst) & 1u)) err = 1;
+        int kd = t.Kd;
+        if (src2 >= 0) { kd |= ksplit << 16; flags |= (src2 << 8) | (off2 << 12); }
+        push(sfb::TR_LINEAR, src, dst, kd, t.N, (int)t.w, (int)t.b, flags);
+        touched = 0;                     // cluster barrier
+    }
+    void attn(int src, int dst, int D, int heads) { push(sfb::TR_ATTN, src, dst, D, heads); touched |= (1u << src) | (1u << dst); }
+    void lstm(int g, int c, int h, int H) { push(sfb::TR_LSTM, g, c, h, H); touched |= (1u << g) | (1u << c) | (1u << h); }
+};
+
+int tr_program(const sfb_tr_weights* w, int D, const TrLayout& L, int K, long long prev_clip_stride, int use_predictor,
+               sfb::TrParams* p) {
+    TrBuilder b{p};
+    p->nops = 0;
+    if (L.floats >= (1LL << 31)) return SFB_E_BAD_SHAPE;
+    if (prev_clip_stride >= (1LL << 31) || prev_clip_stride < 0) return SFB_E_BAD_SHAPE;
+    const bool rnn = use_predictor && w->rnn_hidden > 0;
+    const int H = w->rnn_hidden, SB = sfb::TR_NBUF - 1;       // the LSTM state waits in the last buffer: [c | h]
+    int cur = 0;
+    // every input of the step is fetched up front (one exposed global-load latency instead of three)
+    b.load(cur, 0, D, D, 0, prev_clip_stride, rnn ? sfb::TR_F_NOSYNC : 0);
+    if (rnn) {
+        b.load(SB, 1, H, H, H, -1, sfb::TR_F_NOSYNC);
+        b.load(SB, 2, H, H, 0, -1, 0);
+        b.reserved = 1u << SB;
+    }
+    auto bit = [](int i) { return 1u << i; };
+    if (use_predictor && w->pred_type == SFB_TR_TRANSFORMER) {
+        for (int l = 0; l < w->num_layers; ++l) {
+            if (w->norm_first) {
+                int y = b.pick(bit(cur));
+                b.ln(cur, y, L.n1[l], 0);
+                int z = b.pick(bit(cur) | bit(y));
+                b.linear(y, z, L.qkv[l], 0);
+                y = b.pick(bit(cur) | bit(z));
+                b.attn(z, y, D, w->num_heads);
+                b.linear(y, cur, L.wo[l], sfb::TR_F_ADD);
+                y = b.pick(bit(cur));
+                b.ln(cur, y, L.n2[l], 0);
+                z = b.pick(bit(cur) | bit(y));
+                b.linear(y, z, L.w1[l], sfb::TR_F_RELU);
+                b.linear(z, cur, L.w2[l], sfb::TR_F_ADD);
+            } else {
+                int z = b.pick(bit(cur));
+                b.linear(cur, z, L.qkv[l], 0);
+                int y = b.pick(bit(cur) | bit(z));
+                b.attn(z, y, D, w->num_heads);
+                b.linear(y, cur, L.wo[l], sfb::TR_F_ADD);
+                b.ln(cur, cur, L.n1[l], 0);
+                z = b.pick(bit(cur));
+                b.linear(cur, z, L.w1[l], sfb::TR_F_RELU);
+                b.linear(z, cur, L.w2[l], sfb::TR_F_ADD);
+                b.ln(cur, cur, L.n2[l], 0);
+            }
+        }
+    } else if (use_predictor && w->pred_type == SFB_TR_MLP) {
+        int y = b.pick(bit(cur));
+        b.ln(cur, y, L.mlp_ln, 0);
+        int z = b.pick(bit(cur) | bit(y));
+        b.linear(y, z, L.mlp0, sfb::TR_F_RELU);
+        const int skip = w->norm_first ? y : cur;
+        b.linear(z, skip, L.mlp2, sfb::TR_F_ADD);
+        cur = skip;
+    }
+    if (rnn) {
+        int z = b.pick(bit(cur));
+        b.linear(cur, z, L.gates, 0, SB, H, D);            // gates = [x ; h] [W_ih | W_hh]^T + b_ih + b_hh
+        int hb = b.pick(bit(z));
+        b.lstm(z, SB, hb, H);
+        b.reserved = 0;
+        int y = b.pick(bit(hb));
+        b.linear(hb, y, L.outp, 0);
+        cur = y;
+    }
+    {
+        int z = b.pick(bit(cur));
+        b.linear(cur, z, L.kd0, 0);
+        cur = z;
+        if (w->kernel_mlp) {
+            b.ln(cur, cur, L.kdn, sfb::TR_F_RELU);
+            int x = b.pick(bit(cur));
+            b.linear(cur, x, L.kd3, 0);
+            cur = x;
+        }
+    }
+    b.push(sfb::TR_STORE, cur, 0, 2 * D, 2 * D, 0, 0, sfb::TR_F_NOSYNC);
+    b.push(sfb::TR_SAMPLE, cur, D);
+    (void)K;
+    return b.err ? SFB_E_BAD_SHAPE : SFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t sfb_transition_workspace_bytes(const sfb_tr_weights* w, int D) {
+    TrLayout L;
+    if (tr_layout(w, D, &L)) return 0;
+    return (size_t)L.floats * sizeof(float);
+}
+
+int sfb_transition_prepare(const sfb_tr_weights* w, int D, void* workspace, size_t workspace_bytes, void* stream) {
+    TrLayout L;
+    int rc = tr_layout(w, D, &L);
+    if (rc) return rc;
+    if (!workspace) return SFB_E_NULL;
+    if (workspace_bytes < (size_t)L.floats * sizeof(float)) return SFB_E_WORKSPACE;
+    if (!aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    float* blob = reinterpret_cast<float*>(workspace);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaSuccess;
+    int missing = 0;
+    auto lin = [&](const TrLinear& t, const float* W, const float* bias) {
+        if (!W || !bias) { missing = 1; return; }
+        if (e == cudaSuccess) e = sfb::tr_pack_weight(W, blob + t.w, t.N, t.Kd, 0, st);
+        if (e == cudaSuccess) e = sfb::tr_pack_vec(bias, nullptr, blob + t.b, t.N, st);
+    };
+    auto norm = [&](const TrNorm& t, const float* g, const float* b) {
+        if (!g || !b) { missing = 1; return; }
+        if (e == cudaSuccess) e = sfb::tr_pack_vec(g, nullptr, blob + t.g, t.W, st);
+        if (e == cudaSuccess) e = sfb::tr_pack_vec(b, nullptr, blob + t.b, t.W, st);
+    };
+    if (w->pred_type == SFB_TR_TRANSFORMER) {
+        for (int l = 0; l < w->num_layers; ++l) {
+            const sfb_ro_layer& s = w->layers[l];
+            lin(L.qkv[l], s.self_attn_in_proj_weight, s.self_attn_in_proj_bias);
+            lin(L.wo[l], s.self_attn_out_proj_weight, s.self_attn_out_proj_bias);
+            lin(L.w1[l], s.linear1_weight, s.linear1_bias);
+            lin(L.w2[l], s.linear2_weight, s.linear2_bias);
+            norm(L.n1[l], s.norm1_weight, s.norm1_bias);
+            norm(L.n2[l], s.norm2_weight, s.norm2_bias);
+        }
+    } else if (w->pred_type == SFB_TR_MLP) {
+        norm(L.mlp_ln, w->ln_weight, w->ln_bias);
+        lin(L.mlp0, w->mlp_0_weight, w->mlp_0_bias);
+        lin(L.mlp2, w->mlp_2_weight, w->mlp_2_bias);
+    }
+    if (w->rnn_hidden > 0) {
+        const int H = w->rnn_hidden;
+        if (!w->rnn_weight_ih_l0 || !w->rnn_weight_hh_l0 || !w->rnn_bias_ih_l0 || !w->rnn_bias_hh_l0) missing = 1;
+        else {
+            // gates = [x ; h] [W_ih | W_hh]^T + (b_ih + b_hh): one k-major matrix of D + H rows
+            if (e == cudaSuccess) e = sfb::tr_pack_weight(w->rnn_weight_ih_l0, blob + L.gates.w, 4 * H, D, 0, st);
+            if (e == cudaSuccess) e = sfb::tr_pack_weight(w->rnn_weight_hh_l0, blob + L.gates.w, 4 * H, H, D, st);
+            if (e == cudaSuccess) e = sfb::tr_pack_vec(w->rnn_bias_ih_l0, w->rnn_bias_hh_l0, blob + L.gates.b, 4 * H, st);
+        }
+        lin(L.outp, w->out_projector_weight, w->out_projector_bias);
+    }
+    lin(L.kd0, w->kernel_dist_0_weight, w->kernel_dist_0_bias);
+    if (w->kernel_mlp) {
+        norm(L.kdn, w->kernel_dist_1_weight, w->kernel_dist_1_bias);
+        lin(L.kd3, w->kernel_dist_3_weight, w->kernel_dist_3_bias);
+    }
+    if (missing) return SFB_E_NULL;
+    if (e != cudaSuccess) return cuda_err(e);
+    return SFB_OK;
+}
+
+int sfb_transition_forward(const sfb_tr_weights* w, int D, int B, int K, const float* prev, long long prev_clip_stride,
+                           int use_predictor, const float* h_in, const float* c_in, const float* noise,
+                           float* dist_out, float* slots_out, float* h_out, float* c_out, const void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    if (B == 0) return SFB_OK;
+    TrLayout L;
+    int rc = tr_layout(w, D, &L);
+    if (rc) return rc;
+    if (!prev || !workspace || !dist_out || !slots_out) return SFB_E_NULL;
+    if (B < 0 || K < 1 || K > 8) return SFB_E_BAD_SHAPE;
+    if (workspace_bytes < (size_t)L.floats * sizeof(float)) return SFB_E_WORKSPACE;
+    if (!aligned16(workspace)) return SFB_E_BAD_ALIGN;
+    if (use_predictor && w->rnn_hidden > 0 && (!h_out || !c_out)) return SFB_E_NULL;
+    DevInfo di;
+    rc = device_info(&di);
+    if (rc) return rc;
+    if (di.cc / 10 != 10) return SFB_E_UNSUPPORTED_ARCH;
+    sfb::TrParams p{};
+    p.blob = reinterpret_cast<const float*>(workspace);
+    p.in[0] = prev; p.in[1] = h_in; p.in[2] = c_in; p.in[3] = noise;
+    p.out[0] = dist_out; p.out[1] = slots_out; p.out[2] = h_out; p.out[3] = c_out;
+    p.B = B; p.K = K;
+    p.prof = g_prof; p.prof_cap = g_prof_cap;
+    p.vec_floats = (int)L.vec_floats;
+    rc = tr_program(w, D, L, K, prev_clip_stride, use_predictor, &p);
+    if (rc) return rc;
+    // one cluster per clip; the cluster splits every LINEAR by output feature (all widths are multiples of 32).  The
+    // largest cluster size whose clusters are all resident at once (a second wave would double the latency).
+    static std::atomic<int> max_clusters[64][3][4];          // [device][row variant][log2 cluster size], 0 = not asked yet
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int rv = K <= 4 ? 0 : (K <= 6 ? 1 : 2);
+    int csize = 1;
+    for (int lg = 3; lg >= 1; --lg) {
+        int n = (dev >= 0 && dev < 64) ? max_clusters[dev][rv][lg].load() : 0;
+        if (n == 0) {
+            n = sfb::transition_max_clusters(K, 1 << lg);
+            if (n <= 0) n = -1;
+            if (dev >= 0 && dev < 64) max_clusters[dev][rv][lg].store(n);
+        }
+        if (n >= B) { csize = 1 << lg; break; }
+    }
+    cudaError_t e = sfb::transition_launch(p, csize, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_err(e);
+    g_launches.fetch_add(1);
     return SFB_OK;
 }
 

@@ -69,6 +69,27 @@ class _ROWeights(ctypes.Structure):
                 ('layers', _ROLayer * RO_MAX_LAYERS)]
 
 
+SFB_TR_NONE, SFB_TR_TRANSFORMER, SFB_TR_MLP = 0, 1, 2
+TR_MAX_LAYERS = 4
+TR_MLP_KEYS = ('ln.weight', 'ln.bias', 'mlp.0.weight', 'mlp.0.bias', 'mlp.2.weight', 'mlp.2.bias')
+TR_RNN_KEYS = ('rnn.weight_ih_l0', 'rnn.weight_hh_l0', 'rnn.bias_ih_l0', 'rnn.bias_hh_l0',
+               'out_projector.weight', 'out_projector.bias')
+TR_KD_KEYS = ('kernel_dist.0.weight', 'kernel_dist.0.bias', 'kernel_dist.1.weight', 'kernel_dist.1.bias',
+              'kernel_dist.3.weight', 'kernel_dist.3.bias')
+
+
+class _TRWeights(ctypes.Structure):
+    """sfb_tr_weights (include/sfb200.h): same field order."""
+    _fields_ = ([('pred_type', ctypes.c_int), ('num_layers', ctypes.c_int), ('num_heads', ctypes.c_int),
+                 ('ffn_dim', ctypes.c_int), ('norm_first', ctypes.c_int), ('layers', _ROLayer * TR_MAX_LAYERS),
+                 ('mlp_hidden', ctypes.c_int)]
+                + [(k.replace('.', '_'), ctypes.c_void_p) for k in TR_MLP_KEYS]
+                + [('rnn_hidden', ctypes.c_int)]
+                + [(k.replace('.', '_'), ctypes.c_void_p) for k in TR_RNN_KEYS]
+                + [('kernel_mlp', ctypes.c_int)]
+                + [(k.replace('.', '_'), ctypes.c_void_p) for k in TR_KD_KEYS])
+
+
 def lib_path():
     return _LIB_PATH
 
@@ -121,6 +142,14 @@ def _bind(path, debug):
     lib.sfb_postproc_mask.restype = c.c_int
     lib.sfb_postproc_mask.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_float,
                                       c.c_void_p]
+    lib.sfb_transition_workspace_bytes.restype = c.c_size_t
+    lib.sfb_transition_workspace_bytes.argtypes = [c.POINTER(_TRWeights), c.c_int]
+    lib.sfb_transition_prepare.restype = c.c_int
+    lib.sfb_transition_prepare.argtypes = [c.POINTER(_TRWeights), c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.sfb_transition_forward.restype = c.c_int
+    lib.sfb_transition_forward.argtypes = [c.POINTER(_TRWeights), c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_longlong,
+                                           c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+                                           c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p]
     return lib
 
 
@@ -158,7 +187,8 @@ def exported_symbols(debug=False):
     names = ['sfb_version', 'sfb_strerror', 'sfb_launch_count', 'sfb_sa_workspace_bytes', 'sfb_sa_prepare',
              'sfb_sa_forward', 'sfb_enc_tail_workspace_bytes', 'sfb_enc_tail_tiles_bytes', 'sfb_enc_tail_prepare',
              'sfb_enc_tail_forward', 'sfb_rollout_workspace_bytes', 'sfb_rollout_prepare',
-             'sfb_rollout_forward', 'sfb_decode_combine', 'sfb_postproc_mask']
+             'sfb_rollout_forward', 'sfb_decode_combine', 'sfb_postproc_mask', 'sfb_transition_workspace_bytes',
+             'sfb_transition_prepare', 'sfb_transition_forward']
     if debug:
         names += ['sfb_debug_set_profile', 'sfb_debug_umma_gemm']
     return names
@@ -548,6 +578,116 @@ class RolloutEngine:
                 int(cond_len or 0), int(flags), self._ws.data_ptr(), ws_bytes, _stream(dev))
         _check(rc)
         return out
+
+
+# --------------------------------------------------------------------------- #
+# SAVi slot transition
+# --------------------------------------------------------------------------- #
+class TransitionEngine:
+    """Per-module launcher state for sfb_transition_prepare / sfb_transition_forward: predictor ->
+    kernel_dist_layer -> sample of reference StoSAVi.encode (savi.py:393-410) as one kernel launch per frame."""
+
+    def __init__(self):
+        self._ws = None
+        self._key = None
+        self._captured = []
+
+    def invalidate(self):
+        self._key = None
+
+    @staticmethod
+    def _pack(spec):
+        """spec -> (_TRWeights, tensors kept alive).  ``spec``: dict(pred_type, num_layers, num_heads, ffn_dim,
+        norm_first, mlp_hidden, rnn_hidden, kernel_mlp, weights={name: CUDA f32 tensor})."""
+        cw = _TRWeights()
+        keep = []
+        W = spec['weights']
+
+        def ptr(name):
+            t = W[name]
+            _require_cuda_f32(name, t)
+            t = t if t.is_contiguous() else t.contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        cw.pred_type = int(spec['pred_type'])
+        cw.num_layers = int(spec.get('num_layers', 0))
+        cw.num_heads = int(spec.get('num_heads', 0))
+        cw.ffn_dim = int(spec.get('ffn_dim', 0))
+        cw.norm_first = int(bool(spec.get('norm_first', True)))
+        cw.mlp_hidden = int(spec.get('mlp_hidden', 0))
+        cw.rnn_hidden = int(spec.get('rnn_hidden', 0))
+        cw.kernel_mlp = int(bool(spec.get('kernel_mlp', True)))
+        if cw.pred_type == SFB_TR_TRANSFORMER:
+            if not 1 <= cw.num_layers <= TR_MAX_LAYERS:
+                raise SfbError(f'transition: {cw.num_layers} predictor layers (max {TR_MAX_LAYERS})')
+            for i in range(cw.num_layers):
+                for k in RO_LAYER_KEYS:
+                    setattr(cw.layers[i], k.replace('.', '_'), ptr(f'layers.{i}.{k}'))
+        elif cw.pred_type == SFB_TR_MLP:
+            for k in TR_MLP_KEYS:
+                setattr(cw, k.replace('.', '_'), ptr(k))
+        if cw.rnn_hidden > 0:
+            for k in TR_RNN_KEYS:
+                setattr(cw, k.replace('.', '_'), ptr(k))
+        for k in (TR_KD_KEYS if cw.kernel_mlp else TR_KD_KEYS[:2]):
+            setattr(cw, k.replace('.', '_'), ptr(k))
+        return cw, keep
+
+    @staticmethod
+    def supported(spec, D):
+        """True if the kernel covers this structure (layer widths <= 1024, multiples of 32, ...)."""
+        try:
+            cw, _ = TransitionEngine._pack(spec)
+        except (SfbError, KeyError):
+            return False
+        return int(load().sfb_transition_workspace_bytes(ctypes.byref(cw), int(D))) > 0
+
+    def forward(self, spec, prev, use_predictor, B, state=None, noise=None):
+        """prev: [B, K, D] previous slots, or [1, K, D] rows shared by every clip (init latents, use_predictor False).
+        state: None or (h, c) with B*K rows of rnn_hidden.  Returns (dist [B,K,2D], slots0 [B,K,D], new_state)."""
+        lib = load()
+        _require_cuda_f32('prev', prev)
+        if prev.dim() != 3 or prev.shape[0] not in (1, B):
+            raise SfbError(f'prev must be [B, K, D] or [1, K, D], got {tuple(prev.shape)}')
+        prev = prev.contiguous()
+        K, D = prev.shape[1], prev.shape[2]
+        dev = prev.device
+        cstride = K * D if (prev.shape[0] == B and B > 1) else 0
+        cw, keep = self._pack(spec)
+        ws_bytes = int(lib.sfb_transition_workspace_bytes(ctypes.byref(cw), D))
+        if ws_bytes == 0 or K > 8:
+            raise SfbError(f'unsupported transition structure (D={D}, K={K})')
+        H = cw.rnn_hidden
+        rnn = bool(use_predictor) and H > 0
+        h_in = c_in = h_out = c_out = None
+        if rnn:
+            if state is not None:
+                h_in, c_in = (t.reshape(B * K, H).contiguous() for t in state)
+                _require_cuda_f32('h', h_in)
+                _require_cuda_f32('c', c_in)
+            h_out = torch.empty((B * K, H), dtype=torch.float32, device=dev)
+            c_out = torch.empty((B * K, H), dtype=torch.float32, device=dev)
+        if noise is not None:
+            _require_cuda_f32('noise', noise)
+            noise = noise.contiguous()
+        dist = torch.empty((B, K, 2 * D), dtype=torch.float32, device=dev)
+        slots = torch.empty((B, K, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            if self._ws is None or self._ws.device != dev or self._ws.numel() < ws_bytes:
+                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                self._key = None
+            if torch.cuda.is_current_stream_capturing() and not any(w is self._ws for w in self._captured):
+                self._captured.append(self._ws)
+            key = _weights_key(keep)
+            if key != self._key:
+                _check(lib.sfb_transition_prepare(ctypes.byref(cw), D, self._ws.data_ptr(), ws_bytes, _stream(dev)))
+                self._key = key
+            p = lambda t: None if t is None else t.data_ptr()
+            _check(lib.sfb_transition_forward(ctypes.byref(cw), D, B, K, prev.data_ptr(), cstride, int(bool(use_predictor)),
+                                              p(h_in), p(c_in), p(noise), dist.data_ptr(), slots.data_ptr(), p(h_out),
+                                              p(c_out), self._ws.data_ptr(), ws_bytes, _stream(dev)))
+        return dist, slots, ((h_out, c_out) if rnn else None)
 
 
 # --------------------------------------------------------------------------- #
