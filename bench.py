@@ -277,6 +277,60 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def model_variants(dev, ro, iters=5):
+    """next to the hot-path figure (H, the headline `value`) the same shapes through the model
+    classes, device-resident inputs, this GPU only.  (E): images -> StoSAVi.encode (cuDNN CNN, fused encoder tail,
+    then per frame the transition kernel + Slot Attention -- the frames of a clip are a serial chain in SAVi, unlike
+    (H) where the 384 frames are one batch) -> SlotRollouter.  (E+D): plus StoSAVi.decode of the predicted slots
+    (cuDNN deconvolutions + the decode_combine kernel)."""
+    import torch
+    from slotformer_b200 import engine
+    from slotformer_b200.base_slots.models import StoSAVi
+    B, T_in, T_out, K, D = (WL[k] for k in ('B', 'T_in', 'T_out', 'K', 'D'))
+    torch.manual_seed(0)
+    savi = StoSAVi(
+        resolution=(128, 128), clip_len=T_in,
+        slot_dict=dict(num_slots=K, slot_size=D, slot_mlp_size=WL['Dm'], num_iterations=WL['iters'], kernel_mlp=True),
+        enc_dict=dict(enc_channels=(3, 64, 64, 64, 64), enc_ks=5, enc_out_channels=WL['C'], enc_norm=''),
+        dec_dict=dict(dec_channels=(D, 64, 64, 64, 64), dec_resolution=(8, 8), dec_ks=5, dec_norm=''),
+        pred_dict=dict(pred_type='transformer', pred_rnn=True, pred_norm_first=True, pred_num_layers=2,
+                       pred_num_heads=4, pred_ffn_dim=4 * D, pred_sg_every=None),
+        loss_dict=dict(use_post_recon_loss=True, kld_method='none')).to(dev).eval()
+    img = torch.rand((B, T_in, 3, 128, 128), device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 2 - 1
+
+    def run_e(decode):
+        savi._reset_rnn()
+        _, slots, _ = savi.encode(img)
+        pred = ro(slots, T_out)
+        if decode:
+            flat = pred.flatten(0, 1)
+            for i in range(0, flat.shape[0], 128):          # decoder activations: 128 frames x K slots per slice
+                savi.decode(flat[i:i + 128])
+        return pred
+
+    out = {}
+    with torch.no_grad():
+        for key, decode in (('E', False), ('E+D', True)):
+            for _ in range(2):
+                run_e(decode)
+            torch.cuda.synchronize(dev)
+            n0 = engine.launch_count()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                pred = run_e(decode)
+            b.record()
+            torch.cuda.synchronize(dev)
+            assert torch.isfinite(pred).all()
+            ms = a.elapsed_time(b) / iters
+            out[key] = {'ms_per_step': ms, 'value': frames_per_step() / (ms * 1e-3), 'unit': UNIT,
+                        'sfb_launches_per_step': (engine.launch_count() - n0) // iters}
+    out['what'] = ('(E) images [64, 6, 3, 128, 128] -> StoSAVi.encode (cuDNN CNN + sfb encoder tail, then 6 serial frames of '
+                   'sfb transition + Slot Attention on 64 frames each) -> sfb rollout; (E+D) + StoSAVi.decode of the 640 predicted '
+                   'frames (cuDNN deconvolutions + sfb decode_combine); device-resident inputs, random-init weights')
+    return out
+
+
 # ---- GPU arm ----------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -293,6 +347,8 @@ def run_ours(args):
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from slotformer_b200.parallel import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local)        # before any pinned allocation: host buffers land on the GPU's NUMA node
     # rank 0 prints ONE JSON line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION in this image's environment,
     # printed with printf when the communicator is created) is sent to stderr instead
     saved_stdout = None
@@ -513,6 +569,8 @@ def run_ours(args):
             grid = e2e_route('grid')
             grid['note'] = 'round-1 route: host fp32 feature grid [384, 4096, 128] (806 MB per step), no encoder tail on the device'
             e2e['feature_grid_route'] = grid
+            e2e['host_affinity'] = (f'{len(numa_cpus)} CPUs local to GPU {local} (NVML), set before the pinned allocations'
+                                    if numa_cpus else 'not bound')
 
     if rank != 0:
         if world > 1:
@@ -554,6 +612,8 @@ def run_ours(args):
     if e2e is not None:
         line['e2e'] = e2e
     if world == 1 and not args.no_cpu_baseline:
+        if not args.no_variants:
+            line['variants'] = model_variants(dev, ro)
         line['gpu_eager_baseline'] = gpu_eager_baseline(dev)
         line['cpu_baseline'] = cpu_baseline()
     print(json.dumps(line))
@@ -569,6 +629,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-variants', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -5,8 +5,37 @@ collective: every rank runs the kernels on its own contiguous shard; ``gather_cl
 collecting results on every rank (e.g. rank-0 file writing).  Training adds exactly one gradient
 all-reduce per step over a single flattened buffer (``allreduce_gradients``), replacing the DDP
 wrap the reference gets from nerv (scripts/train.py:65-76, sbatch_run.sh:36-42)."""
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (and the threads it starts later) to the CPUs NVML reports as local to the GPU, so that pinned
+    host buffers allocated afterwards are first-touched on the GPU's own NUMA node and H2D / D2H copies do not cross
+    the socket interconnect (8 ranks feeding 8 GPUs from one node is host-bandwidth bound).
+    Returns the CPU set, or None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = int(device_index)
+        if visible:
+            ids = [v.strip() for v in visible.split(',') if v.strip()]
+            if idx < len(ids) and ids[idx].isdigit():
+                idx = int(ids[idx])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
 
 
 def shard_bounds(n_items, rank, world_size):
