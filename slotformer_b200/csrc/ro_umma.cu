@@ -22,7 +22,7 @@
 namespace sfb {
 
 static constexpr int RU_TILE_BYTES = 16384;                 // one 128 x 64 weight tile
-static constexpr int RU_HPAD = 16;                          // fp32 pad of a residual-stream row (bank spread for 4-lane row groups)
+static constexpr int RU_HPAD = 4;                         // fp32 pad of a residual-stream row (bank spread for 4-lane row groups)
 static constexpr int RU_MAX_STAGE_TILES = 2;                // k-adjacent tiles per ring stage: 1 or 2 (plan)
 static constexpr int RU_TILE_HALVES = 8192;
 static constexpr int RU_SYNC_THREADS = RO_THREADS + 32;   // compute warps + MMA warp
