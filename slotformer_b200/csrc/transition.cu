@@ -237,7 +237,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) transition_kernel(const TrParam
     // inside the steps)
     for (int i = tid * 4; i < p.vec_floats; i += TR_THREADS * 4)
         *reinterpret_cast<float4*>(vec + i) = __ldg(reinterpret_cast<const float4*>(p.blob + i));
-    __syncthreads();
+    // every CTA of the cluster has started before any peer writes into its shared memory (racecheck: "block that might
+    // not have entered yet" on the first LINEAR without this)
+    if (csize > 1) cluster_barrier_all(); else __syncthreads();
     const bool do_prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
     for (int ip = 0; ip < p.nops; ++ip) {
         const TrOp op = s_ops[ip];
