@@ -175,6 +175,31 @@ def test_savi_frame_loop_cuda_graph_matches_eager():
         assert not torch.equal(new[1], got[1])
 
 
+@pytest.mark.gpu
+def test_savi_graphs_survive_workspace_growth():
+    """a captured frame loop holds the engines' workspace pointers.  B = 2, then B = 8 (the
+    workspaces are re-allocated), then B = 2 again replays the OLD graph: its workspaces must still be alive and its
+    results must equal the eager loop."""
+    from slotformer_b200.base_slots.models import StoSAVi
+    m = W.build_savi(StoSAVi).cuda()
+    small = W.savi_input().cuda()                                   # [2, 3, 3, 64, 64]
+    big = torch.cat([small, small.flip(0), small * 0.5, small.flip(1)], dim=0).contiguous()
+
+    def run(x, graph):
+        m.use_cuda_graph = graph
+        m.predictor.reset()
+        return m.encode(x)[1]
+
+    with torch.no_grad():
+        ref_small, ref_big = run(small, False), run(big, False)
+        a = run(small, True)
+        b = run(big, True)
+        junk = [torch.full((1 << 22,), float('nan'), device='cuda') for _ in range(8)]   # reuse of any freed block shows
+        c = run(small, True)
+        del junk
+        assert torch.equal(a, ref_small) and torch.equal(b, ref_big) and torch.equal(c, ref_small)
+
+
 def _steve_gold():
     return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'steve.npz'))
 
