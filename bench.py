@@ -277,7 +277,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def model_variants(dev, ro, iters=5):
+def model_variants(dev, ro, iters=7):
     """next to the hot-path figure (H, the headline `value`) the same shapes through the model
     classes, device-resident inputs, this GPU only.  (E): images -> StoSAVi.encode (cuDNN CNN, fused encoder tail,
     then per frame the transition kernel + Slot Attention -- the frames of a clip are a serial chain in SAVi, unlike
@@ -315,14 +315,16 @@ def model_variants(dev, ro, iters=5):
                 run_e(decode)
             torch.cuda.synchronize(dev)
             n0 = engine.launch_count()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(iters):
+            times = []
+            for _ in range(iters):                       # per-call events, median: the host launches ~100 cuDNN / glue kernels per call
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
                 pred = run_e(decode)
-            b.record()
-            torch.cuda.synchronize(dev)
+                b.record()
+                torch.cuda.synchronize(dev)
+                times.append(a.elapsed_time(b))
             assert torch.isfinite(pred).all()
-            ms = a.elapsed_time(b) / iters
+            ms = float(np.median(times))
             out[key] = {'ms_per_step': ms, 'value': frames_per_step() / (ms * 1e-3), 'unit': UNIT,
                         'sfb_launches_per_step': (engine.launch_count() - n0) // iters}
     out['what'] = ('(E) images [64, 6, 3, 128, 128] -> StoSAVi.encode (cuDNN CNN + sfb encoder tail, then 6 serial frames of '
