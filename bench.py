@@ -277,6 +277,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def build_savi(dev):
+    """StoSAVi of the OBJ3D config (savi_obj3d_params.py:38-72) at 128 x 128, K = 6, random-init weights."""
+    import torch
+    from slotformer_b200.base_slots.models import StoSAVi
+    K, D = WL['K'], WL['D']
+    torch.manual_seed(0)
+    return StoSAVi(
+        resolution=(128, 128), clip_len=WL['T_in'],
+        slot_dict=dict(num_slots=K, slot_size=D, slot_mlp_size=WL['Dm'], num_iterations=WL['iters'], kernel_mlp=True),
+        enc_dict=dict(enc_channels=(3, 64, 64, 64, 64), enc_ks=5, enc_out_channels=WL['C'], enc_norm=''),
+        dec_dict=dict(dec_channels=(D, 64, 64, 64, 64), dec_resolution=(8, 8), dec_ks=5, dec_norm=''),
+        pred_dict=dict(pred_type='transformer', pred_rnn=True, pred_norm_first=True, pred_num_layers=2,
+                       pred_num_heads=4, pred_ffn_dim=4 * D, pred_sg_every=None),
+        loss_dict=dict(use_post_recon_loss=True, kld_method='none')).to(dev).eval()
+
+
 def model_variants(dev, ro, iters=7):
     """next to the hot-path figure (H, the headline `value`) the same shapes through the model
     classes, device-resident inputs, this GPU only.  (E): images -> StoSAVi.encode (cuDNN CNN, fused encoder tail,
@@ -285,17 +301,8 @@ def model_variants(dev, ro, iters=7):
     (cuDNN deconvolutions + the decode_combine kernel)."""
     import torch
     from slotformer_b200 import engine
-    from slotformer_b200.base_slots.models import StoSAVi
     B, T_in, T_out, K, D = (WL[k] for k in ('B', 'T_in', 'T_out', 'K', 'D'))
-    torch.manual_seed(0)
-    savi = StoSAVi(
-        resolution=(128, 128), clip_len=T_in,
-        slot_dict=dict(num_slots=K, slot_size=D, slot_mlp_size=WL['Dm'], num_iterations=WL['iters'], kernel_mlp=True),
-        enc_dict=dict(enc_channels=(3, 64, 64, 64, 64), enc_ks=5, enc_out_channels=WL['C'], enc_norm=''),
-        dec_dict=dict(dec_channels=(D, 64, 64, 64, 64), dec_resolution=(8, 8), dec_ks=5, dec_norm=''),
-        pred_dict=dict(pred_type='transformer', pred_rnn=True, pred_norm_first=True, pred_num_layers=2,
-                       pred_num_heads=4, pred_ffn_dim=4 * D, pred_sg_every=None),
-        loss_dict=dict(use_post_recon_loss=True, kld_method='none')).to(dev).eval()
+    savi = build_savi(dev)
     img = torch.rand((B, T_in, 3, 128, 128), device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 2 - 1
 
     def run_e(decode):
@@ -571,6 +578,55 @@ def run_ours(args):
             grid = e2e_route('grid')
             grid['note'] = 'round-1 route: host fp32 feature grid [384, 4096, 128] (806 MB per step), no encoder tail on the device'
             e2e['feature_grid_route'] = grid
+            # The user-level call one step further up: host IMAGES -> StoSAVi.encode (cuDNN CNN, sfb encoder tail, per
+            # frame sfb transition + Slot Attention) -> sfb rollout -> host.  5.3x fewer bytes cross PCIe, the device does
+            # the CNN: the route that is not bound by the host's aggregate H2D bandwidth when 8 ranks share it.
+            savi = build_savi(dev)
+            h_img = torch.empty((B, T_in, 3, 128, 128), dtype=torch.float32, pin_memory=True)
+            h_img.copy_(torch.rand(h_img.shape, generator=torch.Generator().manual_seed(11 + rank)) * 2 - 1)
+            d_img = [torch.empty(h_img.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            h_s = torch.empty((B, T_in, K, D), dtype=torch.float32, pin_memory=True)
+            h_p = torch.empty((B, T_out, K, D), dtype=torch.float32, pin_memory=True)
+            cur = torch.cuda.current_stream(dev)
+
+            def image_steps(n):
+                evs = [None, None]
+                with torch.cuda.stream(copy_stream):
+                    d_img[0].copy_(h_img, non_blocking=True)
+                    evs[0] = torch.cuda.Event(); evs[0].record(copy_stream)
+                for i in range(n):
+                    sl = i & 1
+                    if i + 1 < n:                          # next step's images while this step computes
+                        copy_stream.wait_stream(cur)
+                        with torch.cuda.stream(copy_stream):
+                            d_img[sl ^ 1].copy_(h_img, non_blocking=True)
+                            evs[sl ^ 1] = torch.cuda.Event(); evs[sl ^ 1].record(copy_stream)
+                    cur.wait_event(evs[sl])
+                    savi._reset_rnn()
+                    _, slots_i, _ = savi.encode(d_img[sl])
+                    pred_i = ro(slots_i, T_out)
+                    h_s.copy_(slots_i, non_blocking=True)
+                    h_p.copy_(pred_i, non_blocking=True)
+                torch.cuda.synchronize(dev)
+
+            image_steps(2)
+            sync_all()
+            n_img = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            image_steps(n_img)
+            dt = (time.perf_counter() - t0) / n_img
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            assert torch.isfinite(h_p).all() and torch.isfinite(h_s).all()
+            e2e['image_route'] = {
+                'value': world * frames_per_step() / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h_img.numel() * 4),
+                'd2h_bytes_per_step': int(h_s.numel() * 4 + h_p.numel() * 4), 'ms_per_step': dt * 1e3, 'steps': n_img,
+                'note': 'host images [64, 6, 3, 128, 128] fp32 -> StoSAVi.encode (cuDNN CNN + sfb encoder tail, 6 serial frames of '
+                        'sfb transition + Slot Attention) -> sfb rollout -> host slots + predictions; H2D of step i+1 overlaps step i'}
+            del savi, d_img
+            torch.cuda.empty_cache()
             e2e['host_affinity'] = (f'{len(numa_cpus)} CPUs local to GPU {local} (NVML), set before the pinned allocations'
                                     if numa_cpus else 'not bound')
 

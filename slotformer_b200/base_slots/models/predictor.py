@@ -82,7 +82,12 @@ class RNNPredictorWrapper(Predictor):
         out = self.base_predictor(x)
         shape = out.shape
         if not (out.is_cuda and torch.cuda.is_current_stream_capturing()):
-            self.rnn.flatten_parameters()       # (inside a CUDA-graph capture it would move the weights into the graph's pool)
+            # (inside a CUDA-graph capture it would move the weights into the graph's pool.)  flatten_parameters() allocates
+            # a new flat buffer on every call: once per set of weight addresses is enough
+            ptrs = tuple(w.data_ptr() for w in self.rnn._flat_weights)
+            if self.__dict__.get('_flat_ptrs') != ptrs:
+                self.rnn.flatten_parameters()
+                self.__dict__['_flat_ptrs'] = tuple(w.data_ptr() for w in self.rnn._flat_weights)
         out, self.hidden_state = self.rnn(out.reshape(1, -1, shape[-1]), self.hidden_state)
         self.step += 1
         return self.out_projector(out[0]).view(shape)

@@ -361,7 +361,13 @@ class StoSAVi(BaseModel):
         h_in = self._state_tensors(pred.hidden_state) if stateful else None
         single = stateful and isinstance(pred.hidden_state, torch.Tensor)
         if hasattr(pred, 'rnn'):
-            pred.rnn.flatten_parameters()                   # before the key: flattening re-points the weights once
+            # before the key: flattening re-points the weights.  nn.RNNBase.flatten_parameters() allocates a NEW flat
+            # buffer on every call (the parameters then alternate between two addresses and every other call would
+            # re-capture the graph and re-pack the weights): flatten once per set of weight addresses
+            ptrs = tuple(w.data_ptr() for w in pred.rnn._flat_weights)
+            if self.__dict__.get('_rnn_flat_ptrs') != ptrs:
+                pred.rnn.flatten_parameters()
+                self.__dict__['_rnn_flat_ptrs'] = tuple(w.data_ptr() for w in pred.rnn._flat_weights)
         key = self._graph_key(feats, prev_slots, h_in is not None)
         tiled = isinstance(feats, FeatureTiles)
         raw = feats.data if tiled else feats
