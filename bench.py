@@ -11,12 +11,15 @@ frames/s = B * (T_in + T_out) / time.  Synthetic inputs, seeded weights (tests/g
 
   value   : inputs already resident in HBM, CUDA-event timed, max over ranks (weak scaling:
             every rank runs its own B=64 clips; the path has no data-path collective).
-  e2e     : same step through the module API with HOST (pinned) inputs, every copy inside the timed
-            region.  The host-side input is the CNN encoder's output (the tensor the reference's
-            _get_encoder_out consumes at savi.py:367, [384, 64, 64, 64] fp32, 403 MB): the fused
-            encoder tail (sfb_enc_tail_forward) turns it into the operand tiles
-            of Slot Attention on the device, so the 806 MB fp32 feature grid never crosses PCIe.
-            e2e.feature_grid_route is the round-1 route (host fp32 feature grid) for continuity.
+  e2e     : the same clips end to end through the model API a user calls, HOST (pinned) buffers, every copy
+            inside the timed region: images [64, 6, 3, 128, 128] fp32 (75 MB) -> StoSAVi.encode (cuDNN CNN, the fused
+            encoder tail sfb_enc_tail_forward, per frame sfb_transition_forward + sfb_sa_forward, replayed as one
+            CUDA graph) -> SlotRollouter (sfb_rollout_forward) -> slots + predictions back on the host.
+            e2e.cnn_output_route enters one step later (host input = the CNN encoder's output, the tensor
+            _get_encoder_out consumes at savi.py:367, 404 MB per step) and e2e.feature_grid_route at the operator
+            boundary itself (the fp32 feature grid, 806 MB per step): both are PCIe-bound on one GPU and bound by the
+            host's aggregate H2D bandwidth when 8 ranks share it.
+  variants: SURVEY 8(d) (E) / (E+D): the model-level step with device-resident images, without / with the decoder.
   roofline: the Slot Attention kernel against the measured HBM peak (algorithmic bytes =
             N*C*4 + 2*K*D*4 per frame).
   cpu_baseline / --impl reference: the UNMODIFIED reference modules (oracle/_ref, collected by
@@ -610,6 +613,12 @@ def run_ours(args):
                 torch.cuda.synchronize(dev)
 
             image_steps(2)
+            savi.use_cuda_graph = False                  # one eager step to count the library's kernels (a graph replay hides them)
+            n0 = engine.launch_count()
+            image_steps(1)
+            img_launches = engine.launch_count() - n0
+            savi.use_cuda_graph = True
+            image_steps(1)
             sync_all()
             n_img = max(3, min(args.steps, 10))
             t0 = time.perf_counter()
@@ -620,11 +629,18 @@ def run_ours(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
             assert torch.isfinite(h_p).all() and torch.isfinite(h_s).all()
-            e2e['image_route'] = {
+            image = {
                 'value': world * frames_per_step() / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h_img.numel() * 4),
                 'd2h_bytes_per_step': int(h_s.numel() * 4 + h_p.numel() * 4), 'ms_per_step': dt * 1e3, 'steps': n_img,
-                'note': 'host images [64, 6, 3, 128, 128] fp32 -> StoSAVi.encode (cuDNN CNN + sfb encoder tail, 6 serial frames of '
-                        'sfb transition + Slot Attention) -> sfb rollout -> host slots + predictions; H2D of step i+1 overlaps step i'}
+                'gpu_launches_per_step': int(img_launches),
+                'note': 'the user-level call: pinned host images [64, 6, 3, 128, 128] fp32 -> StoSAVi.encode (cuDNN CNN + sfb encoder '
+                        'tail, 6 serial frames of sfb transition + Slot Attention, one CUDA-graph replay) -> sfb rollout -> host slots + '
+                        'predictions; H2D of step i+1 overlaps step i'}
+            # headline e2e = the image route; the two routes that enter at the operator boundary (PCIe-bound: 404 / 806 MB
+            # per step, and bound by the host's aggregate H2D bandwidth when 8 ranks share it) are kept beside it
+            image['cnn_output_route'] = {k: v for k, v in e2e.items() if k != 'feature_grid_route'}
+            image['feature_grid_route'] = e2e['feature_grid_route']
+            e2e = image
             del savi, d_img
             torch.cuda.empty_cache()
             e2e['host_affinity'] = (f'{len(numa_cpus)} CPUs local to GPU {local} (NVML), set before the pinned allocations'

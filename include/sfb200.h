@@ -158,11 +158,15 @@ size_t sfb_enc_tail_workspace_bytes(int C);
 size_t sfb_enc_tail_tiles_bytes(int frames, int N, int C);
 /* fold + pack the weights into `workspace` (call again when a weight changed) */
 int sfb_enc_tail_prepare(const sfb_enc_tail_weights* w, int C, void* workspace, size_t workspace_bytes, void* stream);
-/* cnn_out [frames, 64, H, W] fp32 (NCHW, frame f at cnn_out + f*frame_stride elements) -> tiles (frame-major,
- * sfb_enc_tail_tiles_bytes(1, H*W, C) bytes per frame), to be passed to sfb_sa_forward as SFB_DTYPE_TILES16.
- * max_ctas: as in sfb_sa_forward. */
+/* sfb_enc_tail_forward flags */
+#define SFB_ET_NHWC 1u /* cnn_out is channels-last: [frames, H, W, 64] in memory (what cuDNN's tensor-core convolutions
+                          write natively, torch.channels_last) instead of [frames, 64, H, W] */
+/* cnn_out [frames, 64, H, W] fp32 (NCHW memory, or NHWC with SFB_ET_NHWC; frame f at cnn_out + f*frame_stride elements)
+ * -> tiles (frame-major, sfb_enc_tail_tiles_bytes(1, H*W, C) bytes per frame), to be passed to sfb_sa_forward as
+ * SFB_DTYPE_TILES16.  max_ctas: as in sfb_sa_forward. */
 int sfb_enc_tail_forward(const float* cnn_out, int64_t frame_stride, int frames, int H, int W, int C, void* tiles,
-                         size_t tiles_bytes, const void* workspace, size_t workspace_bytes, int max_ctas, void* stream);
+                         size_t tiles_bytes, const void* workspace, size_t workspace_bytes, int max_ctas,
+                         unsigned int flags, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Hot path 2: autoregressive slot-Transformer rollout                        */

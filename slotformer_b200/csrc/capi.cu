@@ -272,7 +272,8 @@ int sfb_enc_tail_prepare(const sfb_enc_tail_weights* w, int C, void* workspace, 
 }
 
 int sfb_enc_tail_forward(const float* cnn_out, int64_t frame_stride, int frames, int H, int W, int C, void* tiles,
-                         size_t tiles_bytes, const void* workspace, size_t workspace_bytes, int max_ctas, void* stream) {
+                         size_t tiles_bytes, const void* workspace, size_t workspace_bytes, int max_ctas, unsigned int flags,
+                         void* stream) {
     if (frames == 0) return SFB_OK;
     if (!cnn_out || !tiles || !workspace) return SFB_E_NULL;
     if (frames < 0 || H < 1 || W < 1 || C != 128 || max_ctas < 0) return SFB_E_BAD_SHAPE;
@@ -292,7 +293,7 @@ int sfb_enc_tail_forward(const float* cnn_out, int64_t frame_stride, int frames,
     sfb::SAWorkspace ws;
     sfb::sa_workspace_layout(1, 1, (int)N, C, C, 2 * C, 1, &ws);
     cudaError_t e = sfb::enc_tail_launch(cnn_out, frame_stride, frames, H, W, tiles, reinterpret_cast<const char*>(workspace),
-                                         di.sms, ws.n16 / 128, reinterpret_cast<cudaStream_t>(stream));
+                                         di.sms, ws.n16 / 128, (flags & SFB_ET_NHWC) != 0, reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_err(e);
     g_launches.fetch_add(1);
     return SFB_OK;

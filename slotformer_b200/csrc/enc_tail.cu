@@ -104,6 +104,9 @@ struct EncTailParams {
     float inv_hm1, inv_wm1;    // 1 / (H - 1), 1 / (W - 1)
 };
 
+// NHWC: the CNN output is channels-last ([frames][N pixels][64 channels], what cuDNN's tensor-core convolutions produce
+// natively): the raw stage is two 128-byte-swizzled panels [128 px][32 ch] fp32 instead of one [64 ch][128 px] slab
+template <bool NHWC>
 __global__ void __launch_bounds__(512, 1) enc_tail_kernel(const EncTailParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tbuf = smem + OFF_T;
@@ -156,10 +159,21 @@ __global__ void __launch_bounds__(512, 1) enc_tail_kernel(const EncTailParams p,
             const float* src = reinterpret_cast<const float*>(inbuf + (size_t)b * ET_IN_BYTES) + row;
             float v[ET_CIN];
             float s1 = 0.f, s2 = 0.f;
+            if (NHWC) {
+                const unsigned char* prow = inbuf + (size_t)b * ET_IN_BYTES + row * 128;
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(prow + q * (ET_IN_BYTES / 2) + xo[j]);
+                        v[32 * q + 4 * j] = w.x; v[32 * q + 4 * j + 1] = w.y; v[32 * q + 4 * j + 2] = w.z; v[32 * q + 4 * j + 3] = w.w;
+                    }
+            }
 #pragma unroll
             for (int c = 0; c < ET_CIN; ++c) {
                 const float4 pc = *reinterpret_cast<const float4*>(pos + 4 * c);
-                v[c] = valid ? src[c * ET_TILE_PX] + fmaf(pc.x, yy, fmaf(pc.y, xx, pc.z)) : 0.f;
+                const float raw = NHWC ? v[c] : src[c * ET_TILE_PX];
+                v[c] = valid ? raw + fmaf(pc.x, yy, fmaf(pc.y, xx, pc.z)) : 0.f;
                 s1 += v[c];
                 s2 = fmaf(v[c], v[c], s2);
             }
@@ -290,7 +304,13 @@ __global__ void __launch_bounds__(512, 1) enc_tail_kernel(const EncTailParams p,
                     mbar_wait(&bars[EB_IN_EMPTY + b], ((i >> 1) & 1) ^ 1);
                     if (tif * ET_TILE_PX < p.N) {
                         mbar_arrive_expect_tx(&bars[EB_IN_FULL + b], ET_IN_BYTES);
-                        tma_load_3d(inbuf + (size_t)b * ET_IN_BYTES, &tmap, tif * ET_TILE_PX, 0, f, &bars[EB_IN_FULL + b], pol);
+                        if (NHWC) {
+                            tma_load_3d(inbuf + (size_t)b * ET_IN_BYTES, &tmap, 0, tif * ET_TILE_PX, f, &bars[EB_IN_FULL + b], pol);
+                            tma_load_3d(inbuf + (size_t)b * ET_IN_BYTES + ET_IN_BYTES / 2, &tmap, 32, tif * ET_TILE_PX, f,
+                                        &bars[EB_IN_FULL + b], pol);
+                        } else {
+                            tma_load_3d(inbuf + (size_t)b * ET_IN_BYTES, &tmap, tif * ET_TILE_PX, 0, f, &bars[EB_IN_FULL + b], pol);
+                        }
                     } else {
                         mbar_arrive(&bars[EB_IN_FULL + b]);
                     }
@@ -393,7 +413,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 cudaError_t enc_tail_launch(const float* cnn, long long frame_stride, int frames, int H, int W, void* tiles,
-                            const char* ws, int sms, int tiles_frame, cudaStream_t st) {
+                            const char* ws, int sms, int tiles_frame, bool nhwc, cudaStream_t st) {
     static EncodeTiledFn enc = nullptr;
     if (enc == nullptr) {
         void* sym = nullptr;
@@ -416,19 +436,31 @@ cudaError_t enc_tail_launch(const float* cnn, long long frame_stride, int frames
     // [frames][64 channels][N pixels] fp32 (NCHW): box = 128 pixels x 64 channels, no swizzle (thread = pixel reads
     // consecutive addresses across the warp); pixels beyond N are zero-filled
     CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)ET_CIN, (cuuint64_t)frames};
-    const cuuint64_t gstride[2] = {(cuuint64_t)N * 4, (cuuint64_t)frame_stride * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)ET_TILE_PX, (cuuint32_t)ET_CIN, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(cnn), gdim, gstride, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(enc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ET_SMEM);
+    CUresult cr;
+    if (nhwc) {
+        // [frames][N pixels][64 channels] fp32 (channels-last): box = 32 channels (128 B) x 128 pixels, 128-byte swizzle
+        const cuuint64_t gdim[3] = {(cuuint64_t)ET_CIN, (cuuint64_t)N, (cuuint64_t)frames};
+        const cuuint64_t gstride[2] = {(cuuint64_t)ET_CIN * 4, (cuuint64_t)frame_stride * 4};
+        const cuuint32_t box[3] = {32u, (cuuint32_t)ET_TILE_PX, 1u};
+        cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(cnn), gdim, gstride, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)ET_CIN, (cuuint64_t)frames};
+        const cuuint64_t gstride[2] = {(cuuint64_t)N * 4, (cuuint64_t)frame_stride * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)ET_TILE_PX, (cuuint32_t)ET_CIN, 1u};
+        cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(cnn), gdim, gstride, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    auto kern = nhwc ? enc_tail_kernel<true> : enc_tail_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ET_SMEM);
     if (e != cudaSuccess) return e;
     const int total = frames * p.tiles_frame;
     const int grid = total < sms ? total : sms;
-    enc_tail_kernel<<<grid, 512, ET_SMEM, st>>>(p, tmap);
+    kern<<<grid, 512, ET_SMEM, st>>>(p, tmap);
     return cudaGetLastError();
 }
 

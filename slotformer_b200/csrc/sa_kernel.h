@@ -92,7 +92,7 @@ cudaError_t enc_tail_prep_launch(const float* pos_w, const float* pos_b, const f
                                  const float* w1, const float* b1, const float* w2, const float* b2, char* ws,
                                  cudaStream_t st);
 cudaError_t enc_tail_launch(const float* cnn, long long frame_stride, int frames, int H, int W, void* tiles,
-                            const char* ws, int sms, int tiles_frame, cudaStream_t st);
+                            const char* ws, int sms, int tiles_frame, bool nhwc, cudaStream_t st);
 bool sa_shape_supported(int C, int D, int DM);
 
 }  // namespace sfb

@@ -21,6 +21,7 @@ SFB_SA_SPLIT_ON = 2
 SFB_SA_SPLIT_OFF = 4
 SFB_SA_XHAT_KEEP = 8
 SFB_RO_MMA_SYNC = 1
+SFB_ET_NHWC = 1
 
 SFB_DTYPE_F32 = 0
 SFB_DTYPE_BF16 = 1
@@ -125,7 +126,7 @@ def _bind(path, debug):
     lib.sfb_enc_tail_prepare.argtypes = [c.POINTER(_EncTailWeights), c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
     lib.sfb_enc_tail_forward.restype = c.c_int
     lib.sfb_enc_tail_forward.argtypes = [c.c_void_p, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p,
-                                         c.c_size_t, c.c_void_p, c.c_size_t, c.c_int, c.c_void_p]
+                                         c.c_size_t, c.c_void_p, c.c_size_t, c.c_int, c.c_uint, c.c_void_p]
     lib.sfb_rollout_workspace_bytes.restype = c.c_size_t
     lib.sfb_rollout_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int]
     lib.sfb_rollout_prepare.restype = c.c_int
@@ -377,13 +378,18 @@ class EncoderTailEngine:
         self._key = None
 
     def forward(self, cnn_out, weights, C, max_ctas=0):
-        """cnn_out [F, 64, H, W] f32 (CNN encoder output, NCHW) -> FeatureTiles [F] (N = H*W, C features)."""
+        """cnn_out [F, 64, H, W] f32 (CNN encoder output; NCHW-contiguous or torch.channels_last memory, read as it
+        is) -> FeatureTiles [F] (N = H*W, C features)."""
         lib = load()
         _require_cuda_f32('cnn_out', cnn_out)
         if cnn_out.dim() != 4 or cnn_out.shape[1] != 64:
             raise SfbError(f'cnn_out must be [frames, 64, H, W], got {tuple(cnn_out.shape)}')
-        cnn_out = cnn_out.contiguous()
         F_, _, H, W = cnn_out.shape
+        # channels-last memory (what cuDNN's tensor-core convolutions write) is consumed directly: no NCHW copy
+        nhwc = (H * W > 1 and not cnn_out.is_contiguous()
+                and cnn_out[:1].is_contiguous(memory_format=torch.channels_last) and cnn_out.stride(0) >= 64 * H * W)
+        if not nhwc:
+            cnn_out = cnn_out.contiguous()
         dev = cnn_out.device
         per_frame = int(lib.sfb_enc_tail_tiles_bytes(1, H * W, C))
         ws_bytes = int(lib.sfb_enc_tail_workspace_bytes(C))
@@ -411,7 +417,8 @@ class EncoderTailEngine:
                 _check(lib.sfb_enc_tail_prepare(ctypes.byref(cw), C, self._ws.data_ptr(), ws_bytes, _stream(dev)))
                 self._key = key
             _check(lib.sfb_enc_tail_forward(cnn_out.data_ptr(), cnn_out.stride(0), F_, H, W, C, tiles.data_ptr(),
-                                            tiles.numel() * 2, self._ws.data_ptr(), ws_bytes, int(max_ctas), _stream(dev)))
+                                            tiles.numel() * 2, self._ws.data_ptr(), ws_bytes, int(max_ctas),
+                                            SFB_ET_NHWC if nhwc else 0, _stream(dev)))
         return FeatureTiles(tiles, H * W, C)
 
 

@@ -27,7 +27,7 @@ def test_enc_tail_abi_validates_without_gpu():
     assert lib.sfb_enc_tail_tiles_bytes(1, 400, 128) == 512 * 128 * 2          # ragged: whole 128-pixel tiles of a chunk
     w = engine._EncTailWeights()
     assert lib.sfb_enc_tail_prepare(ctypes.byref(w), 128, None, 0, None) == -5
-    assert lib.sfb_enc_tail_forward(None, 0, 1, 64, 64, 128, None, 0, None, 0, 0, None) == -5
+    assert lib.sfb_enc_tail_forward(None, 0, 1, 64, 64, 128, None, 0, None, 0, 0, 0, None) == -5
 
 
 def _torch_tail(m, cnn):
@@ -53,6 +53,33 @@ def test_tiles_match_the_pytorch_chain():
     got = tiles.to_dense()
     assert torch.isfinite(got).all()
     assert rel_max(got.cpu().numpy(), t_ref.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hw', [(64, 64), (20, 20), (9, 12)])
+def test_channels_last_input_gives_the_same_tiles(hw):
+    """SFB_ET_NHWC: the CNN output in torch.channels_last memory (what cuDNN's tensor-core convolutions write) is read
+    as it is -- bit-identical tiles to the NCHW route (same per-pixel arithmetic, only the TMA boxes differ); also a
+    channels-last slice with a frame stride (frames 1..3 of a larger buffer), ragged grids with zero tail rows."""
+    from slotformer_b200.base_slots.models import StoSAVi
+    from slotformer_b200.base_slots.models.utils import build_grid
+    H, Wd = hw
+    m = W.build_savi(StoSAVi).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(6)
+    cnn = torch.randn((5, 64, H, Wd), device=DEV, generator=gen) * 1.3 - 0.2
+    named = dict(m.named_parameters())
+    wts = {k: named[k] for k in engine.ENC_TAIL_KEYS}
+    eng = engine.EncoderTailEngine()
+    with torch.no_grad():
+        a = eng.forward(cnn, wts, 128)
+        n0 = engine.launch_count()
+        cl = cnn.contiguous(memory_format=torch.channels_last)
+        assert not cl.is_contiguous()
+        b = eng.forward(cl, wts, 128)
+        c = eng.forward(cl[1:4], wts, 128)
+        assert engine.launch_count() - n0 == 2                    # no layout copy in between
+    assert torch.equal(a.data, b.data)
+    assert torch.equal(a.data[1:4], c.data)
 
 
 @pytest.mark.gpu
