@@ -428,13 +428,20 @@ class StoSAVi(BaseModel):
             pred.step += nsteps
         return out[0].clone(), out[1].clone()
 
-    def encode(self, img, prev_slots=None):
-        """img [B, T, 3, H, W] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D], features)."""
+    def encode_features(self, img):
+        """img [B, T, 3, H, W] -> per-pixel features [B, T, N, C] (the first half of ``encode``: CNN + encoder tail; in
+        inference the fp16 operand tiles of the fused tail).  ``encode(img, feats=...)`` takes them back, so a caller
+        can run this stage of clip batch i+1 on another stream while the serial frame loop of batch i is in flight."""
         B, T = img.shape[:2]
         if self._encoder_tail_fusable(img):
-            feats = self._get_encoder_tiles(img.flatten(0, 1)).unflatten(0, (B, T))
-        else:
-            feats = self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
+            return self._get_encoder_tiles(img.flatten(0, 1)).unflatten(0, (B, T))
+        return self._get_encoder_out(img.flatten(0, 1)).unflatten(0, (B, T))
+
+    def encode(self, img, prev_slots=None, feats=None):
+        """img [B, T, 3, H, W] -> (kernel_dist [B,T,K,2D], post_slots [B,T,K,D], features).
+        ``feats``: the result of ``encode_features(img)`` if the caller computed it already."""
+        if feats is None:
+            feats = self.encode_features(img)
         if self.use_cuda_graph and feats.is_cuda and not torch.is_grad_enabled() and not self.training:
             try:
                 dists, slots = self._frame_loop_graphed(feats.contiguous(), prev_slots)
