@@ -175,6 +175,34 @@ def test_savi_frame_loop_cuda_graph_matches_eager():
         assert not torch.equal(new[1], got[1])
 
 
+def test_encode_features_split_equals_encode_on_cpu():
+    """``encode_features`` + ``encode(feats=...)`` (the two stages a caller may put on different streams) == ``encode``;
+    on the CPU both run the stock layers and the differentiable Slot Attention restatement."""
+    from slotformer_b200.base_slots.models import StoSAVi
+    m = W.build_savi(StoSAVi)
+    img = W.savi_input()[:1, :2]
+    with torch.enable_grad():                                   # CPU tensors only run through the autograd restatement
+        m.predictor.reset()
+        d0, s0, f0 = m.encode(img)
+        m.predictor.reset()
+        feats = m.encode_features(img)
+        d1, s1, f1 = m.encode(None, feats=feats)
+    assert torch.equal(f0, f1) and torch.equal(d0, d1) and torch.equal(s0, s1)
+    assert feats.shape == (1, 2, 4096, 128)
+
+
+def test_bind_to_gpu_numa_is_harmless_without_a_gpu():
+    import os
+    from slotformer_b200.parallel import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_numa(0)
+    assert cpus is None or set(cpus) <= before
+    if cpus is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
+
+
 @pytest.mark.gpu
 def test_savi_graphs_survive_workspace_growth():
     """a captured frame loop holds the engines' workspace pointers.  B = 2, then B = 8 (the
