@@ -600,7 +600,8 @@ def run_ours(args):
                 encoder tail (enc_stream: all SMs, ~4 ms), then the serial frame loop + rollout + D2H (current stream:
                 latency-bound, most SMs idle) -- the frame loop of step i runs under the CNN of step i+1."""
                 h2d, enc, feats = [None, None], [None] * n, [None] * n
-                done = [None, None]                       # frame loop of the step that last used image buffer sl
+                done = [None, None]                       # CNN of the step that last used image buffer sl
+                loop_done = [None, None]                  # frame loop + rollout of the step that last used tile buffer sl
                 def stage_copy(i):
                     sl = i & 1
                     with torch.cuda.stream(copy_stream):
@@ -612,7 +613,13 @@ def run_ours(args):
                     sl = i & 1
                     with torch.cuda.stream(enc_stream):
                         enc_stream.wait_event(h2d[sl])
-                        feats[i] = savi.encode_features(d_img[sl])
+                        if enc_graphs[sl] is not None:     # CNN + tail of this image buffer as one graph launch
+                            if loop_done[sl] is not None:
+                                enc_stream.wait_event(loop_done[sl])   # the frame loop two steps back has copied its tiles
+                            enc_graphs[sl][0].replay()
+                            feats[i] = enc_graphs[sl][1]
+                        else:
+                            feats[i] = savi.encode_features(d_img[sl])
                         enc[i] = torch.cuda.Event(); enc[i].record(enc_stream)
                         done[sl] = enc[i]                  # the image buffer is free once the CNN has read it
                 def stage_loop(i):
@@ -623,6 +630,7 @@ def run_ours(args):
                         pred_i = ro(slots_i, T_out)
                         h_s.copy_(slots_i, non_blocking=True)
                         h_p.copy_(pred_i, non_blocking=True)
+                        loop_done[i & 1] = torch.cuda.Event(); loop_done[i & 1].record(loop_stream)
                 loop_stream.wait_stream(cur)
                 stage_copy(0)
                 for i in range(n):
@@ -634,12 +642,23 @@ def run_ours(args):
                 stage_loop(n - 1)
                 torch.cuda.synchronize(dev)
 
+            enc_graphs = [None, None]
+            image_steps(2)
+            # the CNN + encoder-tail stage of each image buffer as ONE CUDA graph (the host issues ~15 launches per step
+            # for it otherwise; on a busy host that, not the GPU, set the step time)
+            for sl in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ft = savi.encode_features(d_img[sl])
+                enc_graphs[sl] = (g, ft)
             image_steps(2)
             savi.use_cuda_graph = False                  # one eager step to count the library's kernels (a graph replay hides them)
+            saved_graphs, enc_graphs = enc_graphs, [None, None]
             n0 = engine.launch_count()
             image_steps(1)
             img_launches = engine.launch_count() - n0
             savi.use_cuda_graph = True
+            enc_graphs = saved_graphs
             image_steps(1)
             sync_all()
             n_img = max(3, min(args.steps, 10))
@@ -663,7 +682,7 @@ def run_ours(args):
             image['cnn_output_route'] = {k: v for k, v in e2e.items() if k != 'feature_grid_route'}
             image['feature_grid_route'] = e2e['feature_grid_route']
             e2e = image
-            del savi, d_img
+            del savi, d_img, enc_graphs, saved_graphs
             torch.cuda.empty_cache()
             e2e['host_affinity'] = (f'{len(numa_cpus)} CPUs local to GPU {local} (NVML), set before the pinned allocations'
                                     if numa_cpus else 'not bound')
