@@ -22,6 +22,9 @@ Reference lines followed (paths relative to /root/reference/slotformer):
                         batch_first=True, activation=relu), eval mode, as built
                         at slotformer.py:72-80
   * GRU cell            torch.nn.GRUCell gate order (r, z, n)
+  * transition          base_slots/models/savi.py:394-403 with predictor.py:20-113 (Transformer / residual-MLP predictor,
+                        LSTM wrapper, torch.nn.LSTM gate order i, f, g, o), kernel_dist_layer savi.py:200-212,
+                        _sample_dist savi.py:355-363 (pinned by tests/golden/transition.npz)
   * decode_combine      base_slots/models/savi.py:519-523 (pinned by tests/golden/decode.npz)
   * postproc_mask       video_prediction/vp_utils.py:20-41 (pinned by tests/golden/decode.npz)
 
@@ -233,6 +236,68 @@ def rollout(hist, weights, pred_len, num_heads, num_layers, mode='slide',
 # --------------------------------------------------------------------------------------------
 # decoder epilogue
 # --------------------------------------------------------------------------------------------
+def _post_ln_encoder_layer(h, w, prefix, num_heads):
+    """torch.nn.TransformerEncoderLayer(norm_first=False): x = LN1(x + SA(x)); x = LN2(x + FF(x))."""
+    B, L, d = h.shape
+    dh = d // num_heads
+    p = prefix
+    qkv = h @ w[p + 'self_attn.in_proj_weight'].T + w[p + 'self_attn.in_proj_bias']
+    q, k, v = (t.reshape(B, L, num_heads, dh).transpose(0, 2, 1, 3) for t in np.split(qkv, 3, axis=-1))
+    att = _softmax(np.einsum('bhid,bhjd->bhij', q, k) / np.sqrt(dh), axis=-1)
+    o = np.einsum('bhij,bhjd->bhid', att, v).transpose(0, 2, 1, 3).reshape(B, L, d)
+    h = layer_norm(h + o @ w[p + 'self_attn.out_proj.weight'].T + w[p + 'self_attn.out_proj.bias'],
+                   w[p + 'norm1.weight'], w[p + 'norm1.bias'])
+    f = np.maximum(h @ w[p + 'linear1.weight'].T + w[p + 'linear1.bias'], 0.0)
+    return layer_norm(h + f @ w[p + 'linear2.weight'].T + w[p + 'linear2.bias'], w[p + 'norm2.weight'], w[p + 'norm2.bias'])
+
+
+def transition(prev_slots, weights, *, pred_type, num_layers=0, num_heads=0, norm_first=True, rnn=False,
+               kernel_mlp=True, state=None, noise=None, dtype=np.float64):
+    """One SAVi slot transition (reference savi.py:394-403): ``latents = predictor(prev_slots)`` (or, with
+    ``pred_type=None``, ``latents = prev_slots``: the first frame's ``init_latents``), ``dist = kernel_dist_layer(latents)``,
+    ``kernels = mu [+ noise * exp(log_var / 2)]``.
+
+    ``weights``: StoSAVi state_dict entries (``predictor.*``, ``kernel_dist_layer.*``).  ``pred_type``: 'transformer'
+    (predictor.py:20-44), 'mlp' (:47-74) or None; ``rnn``: wrapped in RNNPredictorWrapper (:76-113, one LSTM step over
+    the B*K rows, ``state`` = (h, c) [B*K, H] or None for zeros).  Returns (dist [B,K,2D], kernels [B,K,D], new state)."""
+    w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
+    x = np.asarray(prev_slots, dtype=dtype)
+    B, K, D = x.shape
+    new_state = None
+    if pred_type is not None:
+        base = 'predictor.base_predictor.' if rnn else 'predictor.'
+        if pred_type == 'transformer':
+            for i in range(num_layers):
+                p = f'{base}transformer_encoder.layers.{i}.'
+                x = encoder_layer(x, w, p, num_heads, lambda a, bT: a @ bT.T) if norm_first \
+                    else _post_ln_encoder_layer(x, w, p, num_heads)
+        elif pred_type == 'mlp':
+            normed = layer_norm(x, w[base + 'ln.weight'], w[base + 'ln.bias'])
+            hid = np.maximum(normed @ w[base + 'mlp.0.weight'].T + w[base + 'mlp.0.bias'], 0.0)
+            x = hid @ w[base + 'mlp.2.weight'].T + w[base + 'mlp.2.bias'] + (normed if norm_first else x)
+        else:
+            raise ValueError(pred_type)
+        if rnn:
+            H = w['predictor.rnn.weight_hh_l0'].shape[1]
+            h, c = (np.zeros((B * K, H), dtype), np.zeros((B * K, H), dtype)) if state is None \
+                else (np.asarray(state[0], dtype).reshape(B * K, H), np.asarray(state[1], dtype).reshape(B * K, H))
+            g = x.reshape(B * K, D) @ w['predictor.rnn.weight_ih_l0'].T + w['predictor.rnn.bias_ih_l0'] \
+                + h @ w['predictor.rnn.weight_hh_l0'].T + w['predictor.rnn.bias_hh_l0']
+            i_, f_, g_, o_ = np.split(g, 4, axis=-1)                     # torch.nn.LSTM gate order
+            c = _sigmoid(f_) * c + _sigmoid(i_) * np.tanh(g_)
+            h = _sigmoid(o_) * np.tanh(c)
+            new_state = (h, c)
+            x = (h @ w['predictor.out_projector.weight'].T + w['predictor.out_projector.bias']).reshape(B, K, D)
+    dist = x @ w['kernel_dist_layer.0.weight'].T + w['kernel_dist_layer.0.bias']
+    if kernel_mlp:
+        dist = np.maximum(layer_norm(dist, w['kernel_dist_layer.1.weight'], w['kernel_dist_layer.1.bias']), 0.0)
+        dist = dist @ w['kernel_dist_layer.3.weight'].T + w['kernel_dist_layer.3.bias']
+    kernels = dist[..., :D]
+    if noise is not None:
+        kernels = kernels + np.asarray(noise, dtype) * np.exp(0.5 * dist[..., D:])
+    return dist, kernels, new_state
+
+
 def decode_combine(dec_out, dtype=np.float64):
     """Tail of reference StoSAVi.decode (base_slots/models/savi.py:519-523).
 

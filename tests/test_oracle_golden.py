@@ -67,3 +67,36 @@ def test_state_dict_keys_match_reference():
     g = np.load(os.path.join(GOLD, 'ro_tiny.npz'))
     _, w, _ = cases.ro_case('ro_tiny')
     assert set(g['keys'].tolist()) == set(w) | {'enc_t_pe'}
+
+
+@pytest.mark.parametrize('name', ['tr_obj3d', 'tr_clevrer', 'tr_postln', 'tr_plain'])
+def test_transition_oracle_matches_reference(name):
+    """The numpy restatement of the SAVi slot transition (predictor -> kernel_dist_layer -> sample) against the
+    unmodified reference StoSAVi's chain (tests/golden/transition.npz: fp64 evaluation stored as fp32)."""
+    import os
+    import transition_cases as TC
+    from helpers import GOLD
+    from slotformer_b200.base_slots.models import StoSAVi
+    kw, B, steps, _ = TC.CASES[name]
+    g = np.load(os.path.join(GOLD, 'transition.npz'))
+    m = TC.build(StoSAVi, name)                      # the seeded weights the goldens were made with
+    w = {k: v.numpy() for k, v in m.state_dict().items() if k.startswith(('predictor.', 'kernel_dist_layer.', 'init_latents'))}
+    pd = kw['pred_dict']
+    spec = dict(pred_type=pd.get('pred_type', 'transformer'), num_layers=pd.get('pred_num_layers', 0),
+                num_heads=pd.get('pred_num_heads', 0), norm_first=pd['pred_norm_first'], rnn=pd['pred_rnn'],
+                kernel_mlp=kw['slot_dict']['kernel_mlp'])
+    prev, noise = TC.inputs(name)
+    stochastic = kw['loss_dict']['kld_method'] != 'none'
+    state = None
+    for t in range(steps + 1):
+        nz = noise[t] if stochastic else None
+        if t == 0:
+            x0 = np.repeat(w['init_latents'], B, axis=0)
+            dist, init, _ = O.transition(x0, w, **dict(spec, pred_type=None), noise=nz)
+        else:
+            dist, init, state = O.transition(prev[t - 1], w, **spec, state=state, noise=nz)
+        assert np.abs(dist - g[f'{name}.dist'][t]).max() < 2e-7 * np.abs(g[f'{name}.dist'][t]).max() + 1e-7
+        assert np.abs(init - g[f'{name}.init'][t]).max() < 2e-7 * np.abs(g[f'{name}.init'][t]).max() + 1e-7
+    if pd['pred_rnn']:
+        assert np.abs(state[0] - g[f'{name}.h'][0]).max() < 2e-7
+        assert np.abs(state[1] - g[f'{name}.c'][0]).max() < 5e-7
