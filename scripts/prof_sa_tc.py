@@ -20,6 +20,7 @@ buf = torch.zeros(cap, dtype=torch.int64, device=dev)
 for iters, name in ((1, 'FIRST pass only (no x^ store)'), (2, 'FIRST + NEXT')):
     c = dict(B=384, N=4096, C=128, D=128, Dm=256, K=6, iters=iters, mask=False)
     sa = sa_module(c, sa_w, dev)
+    sa.max_ctas = int(os.environ.get('SA_CTAS', '0'))      # e.g. SA_CTAS=84: the batch pipeline's cap
     feats = torch.randn((384, 4096, 128), device=dev); init = torch.randn((384, 6, 128), device=dev)
     with torch.no_grad():
         for _ in range(2): sa(feats, init)
@@ -39,6 +40,13 @@ for iters, name in ((1, 'FIRST pass only (no x^ store)'), (2, 'FIRST + NEXT')):
     ev.sort()
     # the LAST kernel that wrote the buffer wins (iters=2: the NEXT pass overwrote roles 0 / 1); print tiles 8..13
     if not ev: continue
+    # LayerNorm warp 0 (role 2): average clocks per phase over its sub-tiles
+    r2 = [(clk, tag) for clk, role, tag, tile in ev if role == 2]
+    if len(r2) > 16:
+        names = TAGS[2]; acc = {}
+        for (c0, t0_), (c1, t1_) in zip(r2[:-1], r2[1:]):
+            acc.setdefault(f'{names.get(t0_, t0_)} -> {names.get(t1_, t1_)}', []).append(c1 - c0)
+        print('   LN warp 0, mean clocks per transition: ' + '; '.join(f'{k}: {np.mean(v):.0f} (n={len(v)})' for k, v in acc.items()))
     t0 = ev[0][0]
     for clk, role, tag, tile in ev:
         if 8 <= tile <= 12:

@@ -40,6 +40,9 @@ with torch.no_grad():
         feats = tiles.to_dense().contiguous()
         t_sa_grid = timed(lambda: sa(feats, init))
         a, b = sa(tiles, init), sa(feats, init)
+        cnn_cl = cnn.contiguous(memory_format=torch.channels_last)
+        t_tail_cl = timed(lambda: tail.forward(cnn_cl, wts, 128, max_ctas=ctas))
+        print(f'ctas {ctas or 148}: enc_tail on channels-last input (SFB_ET_NHWC) {t_tail_cl:.0f} us', flush=True)
         print(f'ctas {ctas or 148}: enc_tail {t_tail:.0f} us ({frames * 4096 * (64 * 4 + 128 * 2) / t_tail / 1e6:.2f} TB/s in+out), '
               f'SA on tiles {t_sa_tiles:.0f} us, SA on the fp32 grid {t_sa_grid:.0f} us, '
               f'tiles vs grid slots rel {float((a - b).abs().max() / b.abs().max()):.2e}', flush=True)
