@@ -126,6 +126,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* t
                  : "memory");
 }
 
+// the same with a 4-D map [frames][128-byte channel chunks][pixels][channels of a chunk]: ONE instruction fetches all
+// channel chunks of a 32-pixel stage (16 KB) -- the per-box cost of the TMA unit, not HBM, set the arrival rate of the raw
+// stages with one 4 KB box per instruction
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                 " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+                 :: "r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 // arrive whose issue depends on `dep` (a value derived from loaded data): the barrier is signalled only after
 // the loads that produced `dep` have delivered their registers
 __device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float dep) {
@@ -587,9 +598,7 @@ __global__ void __launch_bounds__(512, 1) sa_pass_tc_first_kernel(const SAPassPa
                     unsigned char* dst = stages + (size_t)s * Cfg::STAGE_BYTES;
                     if (px0 < p.N) {
                         mbar_arrive_expect_tx(&bars[TB_FULL + s], Cfg::STAGE_BYTES);
-#pragma unroll
-                        for (int q = 0; q < Cfg::STAGE_BYTES / 4096; ++q)
-                            tma_load_3d(dst + q * 4096, &tmap, q * (128 / EIN), px0, f, &bars[TB_FULL + s], pol);
+                        tma_load_4d(dst, &tmap, 0, px0, 0, f, &bars[TB_FULL + s], pol);
                     } else {
                         mbar_arrive(&bars[TB_FULL + s]);        // nothing to load: the LN warp writes zero rows
                     }
@@ -712,11 +721,13 @@ cudaError_t sa_pass_tc_launch(const SAPassParams& p, bool first, int sms, cudaSt
     const int ein = p.feat_esize;
     const int nfr = p.frame0 + p.nframes;
     CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {(cuuint64_t)TC_C, (cuuint64_t)p.N, (cuuint64_t)nfr};
-    const cuuint64_t gstride[2] = {(cuuint64_t)TC_C * ein, (cuuint64_t)p.feat_bstride * ein};
-    const cuuint32_t box[3] = {(cuuint32_t)(128 / ein), (cuuint32_t)TC_SUB_PX, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = enc(&tmap, ein == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+    // dims (innermost first): channels of a 128-byte chunk, pixels, chunks, frames; the box is a whole 32-pixel stage
+    // [chunks][32 px][128 B] -- the chunk dimension has the SMALLER stride (128 B) than the pixel dimension (C * ein)
+    const cuuint64_t gdim[4] = {(cuuint64_t)(128 / ein), (cuuint64_t)p.N, (cuuint64_t)(TC_C * ein / 128), (cuuint64_t)nfr};
+    const cuuint64_t gstride[3] = {(cuuint64_t)TC_C * ein, 128u, (cuuint64_t)p.feat_bstride * ein};
+    const cuuint32_t box[4] = {(cuuint32_t)(128 / ein), (cuuint32_t)TC_SUB_PX, (cuuint32_t)(TC_C * ein / 128), 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = enc(&tmap, ein == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                            const_cast<void*>(p.feats), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
