@@ -587,83 +587,31 @@ def run_ours(args):
             savi = build_savi(dev)
             h_img = torch.empty((B, T_in, 3, 128, 128), dtype=torch.float32, pin_memory=True)
             h_img.copy_(torch.rand(h_img.shape, generator=torch.Generator().manual_seed(11 + rank)) * 2 - 1)
-            d_img = [torch.empty(h_img.shape, dtype=torch.float32, device=dev) for _ in range(2)]
             h_s = torch.empty((B, T_in, K, D), dtype=torch.float32, pin_memory=True)
             h_p = torch.empty((B, T_out, K, D), dtype=torch.float32, pin_memory=True)
-            cur = torch.cuda.current_stream(dev)
+            from slotformer_b200.pipeline import ClipPipeline
 
-            enc_stream = torch.cuda.Stream(dev)
-            loop_stream = torch.cuda.Stream(dev, priority=-1)     # the latency-bound stage gets SMs as soon as CNN CTAs retire
+            def image_steps(n, clip_pipe):
+                for _ in range(n):
+                    clip_pipe.submit(h_img, h_s, h_p)
+                clip_pipe.drain()
 
-            def image_steps(n):
-                """Three stages on three streams, software-pipelined over the steps: H2D of the images (copy_stream), CNN +
-                encoder tail (enc_stream: all SMs, ~4 ms), then the serial frame loop + rollout + D2H (current stream:
-                latency-bound, most SMs idle) -- the frame loop of step i runs under the CNN of step i+1."""
-                h2d, enc, feats = [None, None], [None] * n, [None] * n
-                done = [None, None]                       # CNN of the step that last used image buffer sl
-                loop_done = [None, None]                  # frame loop + rollout of the step that last used tile buffer sl
-                def stage_copy(i):
-                    sl = i & 1
-                    with torch.cuda.stream(copy_stream):
-                        if done[sl] is not None:
-                            copy_stream.wait_event(done[sl])
-                        d_img[sl].copy_(h_img, non_blocking=True)
-                        h2d[sl] = torch.cuda.Event(); h2d[sl].record(copy_stream)
-                def stage_encode(i):
-                    sl = i & 1
-                    with torch.cuda.stream(enc_stream):
-                        enc_stream.wait_event(h2d[sl])
-                        if enc_graphs[sl] is not None:     # CNN + tail of this image buffer as one graph launch
-                            if loop_done[sl] is not None:
-                                enc_stream.wait_event(loop_done[sl])   # the frame loop two steps back has copied its tiles
-                            enc_graphs[sl][0].replay()
-                            feats[i] = enc_graphs[sl][1]
-                        else:
-                            feats[i] = savi.encode_features(d_img[sl])
-                        enc[i] = torch.cuda.Event(); enc[i].record(enc_stream)
-                        done[sl] = enc[i]                  # the image buffer is free once the CNN has read it
-                def stage_loop(i):
-                    with torch.cuda.stream(loop_stream):
-                        loop_stream.wait_event(enc[i])
-                        savi._reset_rnn()
-                        _, slots_i, _ = savi.encode(None, feats=feats[i])
-                        pred_i = ro(slots_i, T_out)
-                        h_s.copy_(slots_i, non_blocking=True)
-                        h_p.copy_(pred_i, non_blocking=True)
-                        loop_done[i & 1] = torch.cuda.Event(); loop_done[i & 1].record(loop_stream)
-                loop_stream.wait_stream(cur)
-                stage_copy(0)
-                for i in range(n):
-                    if i + 1 < n:
-                        stage_copy(i + 1)
-                    stage_encode(i)
-                    if i > 0:
-                        stage_loop(i - 1)
-                stage_loop(n - 1)
-                torch.cuda.synchronize(dev)
-
-            enc_graphs = [None, None]
-            image_steps(2)
-            # the CNN + encoder-tail stage of each image buffer as ONE CUDA graph (the host issues ~15 launches per step
-            # for it otherwise; on a busy host that, not the GPU, set the step time)
-            for sl in range(2):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    ft = savi.encode_features(d_img[sl])
-                enc_graphs[sl] = (g, ft)
-            image_steps(2)
-            savi.use_cuda_graph = False                  # one eager step to count the library's kernels (a graph replay hides them)
-            saved_graphs, enc_graphs = enc_graphs, [None, None]
+            # one eager step to count the library's kernels (graph replays hide them), then the pipeline of the timed run
+            savi.use_cuda_graph = False
+            counting = ClipPipeline(savi, ro, T_out, dev, capture_encode=False)
+            counting.warmup(h_img)
             n0 = engine.launch_count()
-            image_steps(1)
+            image_steps(1, counting)
             img_launches = engine.launch_count() - n0
+            del counting
             savi.use_cuda_graph = True
-            enc_graphs = saved_graphs
-            image_steps(1)
+            clip_pipe = ClipPipeline(savi, ro, T_out, dev)
+            clip_pipe.warmup(h_img)
+            image_steps(3, clip_pipe)
             sync_all()
             n_img = max(3, min(args.steps, 10))
             t0 = time.perf_counter()
-            image_steps(n_img)
+            image_steps(n_img, clip_pipe)
             dt = (time.perf_counter() - t0) / n_img
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             if world > 1:
@@ -676,13 +624,14 @@ def run_ours(args):
                 'gpu_launches_per_step': int(img_launches),
                 'note': 'the user-level call: pinned host images [64, 6, 3, 128, 128] fp32 -> StoSAVi.encode (cuDNN CNN + sfb encoder '
                         'tail, 6 serial frames of sfb transition + Slot Attention, one CUDA-graph replay) -> sfb rollout -> host slots + '
-                        'predictions; three streams: H2D and CNN + tail of step i+1 overlap the frame loop + rollout of step i'}
+                        'predictions; slotformer_b200.pipeline.ClipPipeline: three streams, H2D and CNN + tail (one CUDA graph) of step i+1 overlap the '
+                        'frame loop + rollout of step i'}
             # headline e2e = the image route; the two routes that enter at the operator boundary (PCIe-bound: 404 / 806 MB
             # per step, and bound by the host's aggregate H2D bandwidth when 8 ranks share it) are kept beside it
             image['cnn_output_route'] = {k: v for k, v in e2e.items() if k != 'feature_grid_route'}
             image['feature_grid_route'] = e2e['feature_grid_route']
             e2e = image
-            del savi, d_img, enc_graphs, saved_graphs
+            del savi, clip_pipe
             torch.cuda.empty_cache()
             e2e['host_affinity'] = (f'{len(numa_cpus)} CPUs local to GPU {local} (NVML), set before the pinned allocations'
                                     if numa_cpus else 'not bound')
