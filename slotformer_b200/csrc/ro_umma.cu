@@ -27,8 +27,8 @@ static constexpr int RU_MAX_STAGE_TILES = 2;                // k-adjacent tiles 
 static constexpr int RU_TILE_HALVES = 8192;
 static constexpr int RU_SYNC_THREADS = RO_THREADS + 32;   // compute warps + MMA warp
 static constexpr int RU_THREADS = RO_THREADS + 128;   // + one warpgroup: TMA producer, MMA issuer, two idle warps
-static constexpr int RU_REGS_COMPUTE = 224;          // setmaxnreg: the epilogue / attention warps take what the
-static constexpr int RU_REGS_SERVICE = 56;           // service warpgroup gives up (8*32*224 + 4*32*56 = 64512)
+static constexpr int RU_REGS_COMPUTE = 232;          // setmaxnreg: the epilogue / attention warps take what the
+static constexpr int RU_REGS_SERVICE = 40;           // service warpgroup gives up (8*32*232 + 4*32*40 = 64512)
 
 struct UOp {
     const __half* base;   // packed matrix (ro_pack2 layout)
