@@ -343,6 +343,67 @@ def model_variants(dev, ro, iters=7):
     return out
 
 
+def config1_variant(dev, iters=20):
+    """BASELINE.json configs[0] -- 'OBJ3D SAVi slot extraction, B=4, 64x64, K=5, 3 iters' (the reference's own CPU-runnable
+    case): StoSAVi(testing=True) on images [4, 6, 3, 64, 64], device-resident; ours (one CUDA-graph replay of the frame
+    loop: per frame the transition kernel + Slot Attention) next to the UNMODIFIED reference StoSAVi (oracle/_ref) with the
+    same state_dict on this GPU (PyTorch eager) and on the host cores.  Extracted slots compared in passing."""
+    import torch
+    from oracle.build_ref import import_ref
+    from slotformer_b200.base_slots.models import StoSAVi
+    kw = dict(
+        resolution=(64, 64), clip_len=6,
+        slot_dict=dict(num_slots=5, slot_size=128, slot_mlp_size=256, num_iterations=3, kernel_mlp=True),
+        enc_dict=dict(enc_channels=(3, 64, 64, 64, 64), enc_ks=5, enc_out_channels=128, enc_norm=''),
+        dec_dict=dict(dec_channels=(128, 64, 64, 64, 64), dec_resolution=(8, 8), dec_ks=5, dec_norm=''),
+        pred_dict=dict(pred_type='transformer', pred_rnn=True, pred_norm_first=True, pred_num_layers=2,
+                       pred_num_heads=4, pred_ffn_dim=512, pred_sg_every=None),
+        loss_dict=dict(use_post_recon_loss=True, kld_method='none'))
+    torch.manual_seed(0)
+    ours = StoSAVi(**kw).to(dev).eval()
+    ref = import_ref()['StoSAVi'](**kw).eval()
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ours.testing = ref.testing = True
+    img = torch.rand((4, 6, 3, 64, 64), generator=torch.Generator().manual_seed(3)) * 2 - 1
+    d_img = img.to(dev)
+    frames = 4 * 6
+
+    def gpu_ms(model):
+        with torch.no_grad():
+            for _ in range(3):
+                out = model({'img': d_img})['post_slots']
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(iters):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = model({'img': d_img})['post_slots']
+                b.record()
+                torch.cuda.synchronize(dev)
+                ts.append(a.elapsed_time(b))
+        return float(np.median(ts)), out
+
+    t_ours, s_ours = gpu_ms(ours)
+    ref = ref.to(dev)
+    t_ref_gpu, s_ref = gpu_ms(ref)
+    err = float((s_ours - s_ref).abs().max() / s_ref.abs().max())
+    ref = ref.cpu()
+    torch.set_num_threads(cpu_threads())
+    with torch.no_grad():
+        ref({'img': img})
+        cs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ref({'img': img})
+            cs.append(time.perf_counter() - t0)
+    t_cpu = float(np.median(cs)) * 1e3
+    return {'workload': 'OBJ3D SAVi slot extraction, B=4, 64x64, K=5, 3 iters, T=6 (StoSAVi.forward, testing=True)',
+            'ours': {'ms_per_step': t_ours, 'value': frames / (t_ours * 1e-3), 'unit': UNIT},
+            'reference_gpu_eager': {'ms_per_step': t_ref_gpu, 'value': frames / (t_ref_gpu * 1e-3), 'unit': UNIT},
+            'reference_cpu': {'ms_per_step': t_cpu, 'value': frames / (t_cpu * 1e-3), 'unit': UNIT, 'cores': cpu_threads()},
+            'slots_rel_err_vs_reference_gpu': err}
+
+
 # ---- GPU arm ----------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -678,6 +739,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         if not args.no_variants:
             line['variants'] = model_variants(dev, ro)
+            line['variants']['config1'] = config1_variant(dev)
         line['gpu_eager_baseline'] = gpu_eager_baseline(dev)
         line['cpu_baseline'] = cpu_baseline()
     print(json.dumps(line))
