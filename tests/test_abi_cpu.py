@@ -109,3 +109,21 @@ def test_modules_keep_reference_state_dict_keys():
         # the sinusoid table the module builds equals the reference's enc_t_pe
         fresh = ro_module(c, w, 'cpu')
         assert (fresh.enc_t_pe.numpy() == g['enc_t_pe']).all()
+
+
+def test_invalidate_kernel_caches_resets_every_launcher():
+    """ADVICE r1 (low): in-place weight updates through ``.data`` do not change the (data_ptr, _version) cache key;
+    ``slotformer_b200.invalidate_kernel_caches(model)`` is the explicit hook."""
+    import slotformer_b200
+    from slotformer_b200.engine import TransitionEngine
+    from slotformer_b200.base_slots.models import StoSAVi
+    import wrapper_cases as W
+    m = W.build_savi(StoSAVi)
+    m.slot_attention._engine._key = ('stale',)
+    m.__dict__['_transition_engine'] = TransitionEngine()
+    m._transition_engine._key = ('stale',)
+    m.__dict__['_loop_graphs'] = {'k': object()}
+    assert slotformer_b200.invalidate_kernel_caches(m) == 3
+    assert m.slot_attention._engine._key is None and m._transition_engine._key is None
+    assert '_loop_graphs' not in m.__dict__
+
