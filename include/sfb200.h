@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SFB_VERSION 200 /* 0.2.0 */
+#define SFB_VERSION 210 /* 0.2.1: sfb_transition_*, flags argument of sfb_enc_tail_forward */
 
 #define SFB_OK 0
 #define SFB_E_BAD_SHAPE (-1)        /* unsupported / inconsistent dimensions            */

@@ -49,7 +49,7 @@ def test_debug_library_exports_the_debug_hooks():
 
 
 def test_version_and_strerror(lib):
-    assert lib.sfb_version() == 200
+    assert lib.sfb_version() == 210
     assert lib.sfb_strerror(0) == b'ok'
     assert b'shape' in lib.sfb_strerror(-1)
     assert b'aligned' in lib.sfb_strerror(-2)
